@@ -1,0 +1,171 @@
+/*
+ * adcensus_b200.h -- C ABI of libadcensus_b200.so, the B200 (sm_100a) drop-in
+ * for the stereo-method hot path of jzbontar/mc-cnn's libadcensus.so.
+ *
+ * The reference exposes this path only as lua_CFunctions registered into the
+ * Lua table `adcensus` (adcensus.cu:2061-2105).  Each `adcensus_<name>` below
+ * is the plain-C core that the Lua face (csrc/lua_face.cu,
+ * luaopen_libadcensus) -- or any other FFI: cgo, ctypes, JNI -- binds for the
+ * Lua function of the same name; arguments are the tensors' raw device
+ * pointers plus the sizes the reference reads from the tensors themselves
+ * (SURVEY.md 8b).  See INTEGRATION.md for the binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous float32 (the reference
+ *     ignores strides: raw THCudaTensor_data + sizes);
+ *   - shapes: features (C,H,W); cost volumes (D,H,W); SGM volumes (H,W,D);
+ *     images / disparity maps (H,W); cross arms (4,H,W);
+ *   - `stream` is a cudaStream_t (0 = legacy default stream, what the
+ *     reference launches on); all work is asynchronous on it unless noted;
+ *   - return 0 on success, a positive cudaError_t, or a negative ADCENSUS_E*
+ *     for arguments the kernels cannot handle (the reference's compiled-out
+ *     device asserts: C <= 128 adcensus.cu:1460, D <= 400 :574, H <= W for
+ *     sgm2's tmp :570).  Nothing here ever falls back to a CPU path.
+ *   - no function keeps a pointer after it returns; the library holds no
+ *     global mutable state apart from a per-device scratch pool that is
+ *     stream-ordered (cudaMallocAsync).
+ */
+#ifndef ADCENSUS_B200_H
+#define ADCENSUS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADCENSUS_EINVAL (-1)   /* bad size / null pointer / unsupported value */
+#define ADCENSUS_ELIMIT (-2)   /* exceeds a documented limit (D, C, ksize ...) */
+
+#define ADCENSUS_MAX_DISP 512      /* sgm2: reference tree-min covers d < 512 (adcensus.cu:579) */
+#define ADCENSUS_MAX_MEDIAN 11     /* median2d: float xs[11*11] (adcensus.cu:1582) */
+
+typedef void *adcensus_stream_t;   /* cudaStream_t */
+
+/* "libadcensus_b200 <version>"; replaces adcensus.version (adcensus.cu:2055-2059) */
+const char *adcensus_version(void);
+
+/* ---- operators of the hot path (one per Lua function) ------------------- */
+
+/* adcensus.StereoJoin(input_L, input_R, output_L, output_R)  adcensus.cu:1455-1498
+ * outL[d,y,x] = outR[d,y,x-d] = -sum_c L[c,y,x]*R[c,y,x-d] for x-d >= 0 (fp32 FMA
+ * chain, c ascending); other entries are left untouched (caller pre-fills NaN,
+ * main.lua:946). */
+int adcensus_StereoJoin(const float *input_L, const float *input_R, float *output_L, float *output_R,
+			int C, int D, int H, int W, adcensus_stream_t stream);
+
+/* adcensus.cross(x0, out, L1, tau1)  adcensus.cu:280-341; out is (4,H,W) */
+int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1, adcensus_stream_t stream);
+
+/* adcensus.cbca(x0c, x1c, vol_in, vol_out, direction)  adcensus.cu:343-400
+ * vol_in must not alias vol_out.  Synchronises `stream` once (it reads back the
+ * longest arm to size its shared-memory tile). */
+int adcensus_cbca(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+		  int D, int H, int W, int direction, adcensus_stream_t stream);
+
+/* adcensus.sgm2(x0, x1, input, output, tmp, pi1, pi2, tau_so, alpha1, sgm_q1,
+ *               sgm_q2, direction)  adcensus.cu:535-697
+ * input/output are (H,W,D); output is accumulated into (+=) in the order right,
+ * left, down, up.  tmp (>= W*D floats) is the reference's line-state scratch; it
+ * is accepted for signature parity and may be NULL (state lives on chip). */
+int adcensus_sgm2(const float *x0, const float *x1, const float *input, float *output, float *tmp,
+		  int H, int W, int D, float pi1, float pi2, float tau_so, float alpha1,
+		  float sgm_q1, float sgm_q2, int direction, adcensus_stream_t stream);
+
+/* adcensus.outlier_detection(d0, d1, outlier, disp_max)  adcensus.cu:878-918 */
+int adcensus_outlier_detection(const float *d0, const float *d1, float *outlier,
+			       int H, int W, int disp_max, adcensus_stream_t stream);
+
+/* adcensus.interpolate_occlusion(d0, outlier) -> out  adcensus.cu:1079-1125
+ * (the Lua face allocates `out` like new_tensor_like, adcensus.cu:40-45) */
+int adcensus_interpolate_occlusion(const float *d0, const float *outlier, float *out,
+				   int H, int W, adcensus_stream_t stream);
+
+/* adcensus.interpolate_mismatch(d0, outlier) -> out  adcensus.cu:1001-1077 */
+int adcensus_interpolate_mismatch(const float *d0, const float *outlier, float *out,
+				  int H, int W, adcensus_stream_t stream);
+
+/* adcensus.subpixel_enchancement(d0, c2, disp_max) -> out  adcensus.cu:1205-1239
+ * c2 is the (disp_max,H,W) cost volume */
+int adcensus_subpixel_enchancement(const float *d0, const float *c2, float *out,
+				   int H, int W, int disp_max, adcensus_stream_t stream);
+
+/* adcensus.median2d(img, kernel_size) -> out  adcensus.cu:1575-1613; odd ksize <= 11 */
+int adcensus_median2d(const float *img, float *out, int H, int W, int kernel_size, adcensus_stream_t stream);
+
+/* adcensus.mean2d(img, kernel, alpha2) -> out  adcensus.cu:1241-1282
+ * kernel is (ksize,ksize), ksize odd */
+int adcensus_mean2d(const float *img, const float *kernel, float *out, int H, int W, int ksize,
+		    float alpha2, adcensus_stream_t stream);
+
+/* adcensus.Normalize_forward(input, norm, output)  adcensus.cu:1284-1333
+ * input/output (N,C,H,W), norm (N,1,H,W) */
+int adcensus_Normalize_forward(const float *input, float *norm, float *output,
+			       int N, int C, int H, int W, adcensus_stream_t stream);
+
+/* adcensus.spatial_argmin(input, output)  adcensus.cu:244-278
+ * input (N,D,H,W) -> output (N,1,H,W), 1-based, strict <, NaN skipped */
+int adcensus_spatial_argmin(const float *input, float *output, int N, int D, int HW, adcensus_stream_t stream);
+
+/* adcensus.ad / adcensus.census  adcensus.cu:62-175 (net-free cost volumes; x0,x1 (nch,H,W)) */
+int adcensus_ad(const float *x0, const float *x1, float *out, int D, int H, int W, int direction,
+		adcensus_stream_t stream);
+int adcensus_census(const float *x0, const float *x1, float *out, int D, int nch, int H, int W,
+		    int direction, adcensus_stream_t stream);
+
+/* ---- the Lua-side tensor ops of stereo_predict (cutorch in the reference) - */
+
+/* vols:fill(0/0)  main.lua:946 */
+int mccnn_fill_nan(float *p, size_t n, adcensus_stream_t stream);
+/* fix_border(net, vol, direction)  main.lua:922-927; n = (window-1)/2 */
+int mccnn_fix_border(float *vol, int D, int H, int W, int n, int direction, adcensus_stream_t stream);
+/* vol:transpose(2,3):transpose(3,4):clone()  main.lua:1008   (D,H,W) -> (H,W,D) */
+int mccnn_transpose_dhw_to_hwd(const float *in, float *out, int D, int H, int W, adcensus_stream_t stream);
+/* vol:copy(out:transpose(3,4):transpose(2,3)):div(4)  main.lua:1020   (H,W,D) -> (D,H,W), /4 */
+int mccnn_transpose_hwd_to_dhw_div4(const float *in, float *out, int D, int H, int W, adcensus_stream_t stream);
+/* _, d = torch.min(vol, 2); d:add(-1)  main.lua:1049-1050: 0-based argmin as float,
+ * first minimum, NaN skipped (the in-repo statement is spatial_argmin) */
+int mccnn_argmin(const float *vol, float *disp, int D, int HW, adcensus_stream_t stream);
+/* gaussian(sigma)  main.lua:528-540: HOST helper; returns ksize, fills out (ksize*ksize) if non-NULL */
+int mccnn_gaussian(double sigma, float *out_host);
+
+/* ---- fused stereo_predict (main.lua:929-1082, arch 'fast') ---------------- */
+
+typedef struct mccnn_params {
+	int L1;
+	float tau1;
+	int cbca_i1, cbca_i2;
+	float pi1, pi2, sgm_q1, sgm_q2, alpha1, tau_so;
+	int sgm_i;
+	double blur_sigma;
+	float blur_t;
+	int border;    /* fix_border n (4 for the 4-layer 3x3 tower, main.lua:382-391,923) */
+	int lr_check;  /* 1: kitti / kitti2015 (main.lua:1054); 0: mb */
+} mccnn_params;
+
+typedef struct mccnn_pipeline mccnn_pipeline;
+
+/* Allocates every device buffer the pipeline needs for (C,D,H,W) on `device`. */
+int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, int W,
+			  const mccnn_params *params, int device);
+void mccnn_pipeline_destroy(mccnn_pipeline *p);
+size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p);
+/* number of kernel launches one run issues (for bench.py's gpu_launches) */
+int mccnn_pipeline_launches_per_run(const mccnn_pipeline *p);
+
+/* Device-resident inputs: featL/featR (C,H,W) unit-norm tower outputs, imgL/imgR
+ * (H,W) standardised images.  disp (H,W) device; volL/volR (D,H,W) device or NULL
+ * (what `-a predict` writes to left.bin/right.bin).  Asynchronous on `stream`. */
+int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const float *featR,
+		       const float *imgL, const float *imgR, float *disp,
+		       float *volL, float *volR, adcensus_stream_t stream);
+
+/* Host-buffer call (what a non-CUDA caller binds): copies inputs H2D, runs,
+ * copies disp back, and returns after the result is in disp_host. */
+int mccnn_pipeline_run_host(mccnn_pipeline *p, const float *featL_host, const float *featR_host,
+			    const float *imgL_host, const float *imgR_host, float *disp_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

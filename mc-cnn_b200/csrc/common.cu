@@ -1,0 +1,27 @@
+// common.cu -- device properties cache, stream-ordered scratch, version string
+#include "common.cuh"
+
+int adc_num_sms()
+{
+	static int sms[64] = {0};
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+	if (!sms[dev & 63]) {
+		int n = 0;
+		if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+		sms[dev & 63] = n;
+	}
+	return sms[dev & 63];
+}
+
+int adc_scratch_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+	return (int)cudaMallocAsync(p, bytes ? bytes : 4, s);
+}
+
+int adc_scratch_free(void *p, cudaStream_t s)
+{
+	return p ? (int)cudaFreeAsync(p, s) : 0;
+}
+
+extern "C" const char *adcensus_version(void) { return "libadcensus_b200 0.1.0 (sm_100a)"; }

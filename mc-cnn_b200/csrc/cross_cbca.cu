@@ -1,0 +1,246 @@
+// cross_cbca.cu -- adcensus.cross and adcensus.cbca for sm_100a.
+//
+// cross (adcensus.cu:280-341): per pixel, the four exclusive arm end-points.
+// Tiny (4*H*W outputs, <= L1 steps each); one thread per (arm, pixel).
+//
+// cbca (adcensus.cu:343-400): cross-based cost aggregation.  The reference does
+// up to (2*L1-1)^2 scattered global loads per output plus 4 float arm loads per
+// support row.  Here:
+//   * the float arm coordinates of both images are packed once per call into one
+//     32-bit word per pixel (4 arm LENGTHS as bytes).  In relative form the
+//     support of output (d,y,x) with xs = x + d*direction is
+//         rows  y - min(U0(y,x),U1(y,xs)) < yy < y + min(D0(y,x),D1(y,xs))
+//         cols  x - min(L0(yy,x),L1(yy,xs)) < xx < x + min(R0(yy,x),R1(yy,xs))
+//     so one __vminu4 of two packed words replaces 4 loads + 2 max/min + 2 cvt;
+//   * a CTA owns a 16x64 pixel tile and loops over a chunk of disparities; the
+//     packed arms of the tile (left image) and of the shifted window (right image)
+//     are loaded into shared memory once per CTA, the volume plane tile (+halo)
+//     once per disparity (shared-memory line stencil), so every tap is an LDS;
+//   * taps are summed in the reference's order (rows outer, columns inner, one
+//     fp32 accumulator, adcensus.cu:361-370) => bit-identical volumes.
+// Roofline: read V + write V (V = 4*D*H*W bytes) per iteration; this exact-order
+// version is bound by shared-memory/FADD issue (one dependent FADD per tap), not
+// by HBM -- see DESIGN.md.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ cross
+__global__ void cross_kernel(const float *__restrict__ img, float *__restrict__ out, int H, int W, int L1, float tau1)
+{
+	long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	long HW = (long)H * W;
+	if (id >= 4 * HW) return;
+	int x = (int)(id % W);
+	int y = (int)((id / W) % H);
+	int dir = (int)(id / HW);
+	int dx = dir == 0 ? -1 : (dir == 1 ? 1 : 0);
+	int dy = dir == 2 ? -1 : (dir == 3 ? 1 : 0);
+	float c = __ldg(img + (long)y * W + x);
+	int xx = x + dx, yy = y + dy;
+	for (;; xx += dx, yy += dy) {
+		if (xx < 0 || xx >= W || yy < 0 || yy >= H) break;            // :307
+		int dist = max(abs(xx - x), abs(yy - y));
+		if (dist == 1) continue;                                       // :310
+		if (fabsf(c - __ldg(img + (long)yy * W + xx)) >= tau1) break;  // :315
+		if (dist >= L1) break;                                         // :318
+	}
+	out[id] = dir <= 1 ? xx : yy;                                      // :320
+}
+
+// ------------------------------------------------------------------ arm packing
+// word = L | R<<8 | U<<16 | D<<24 with L = x - left end-point etc. (all >= 1 for arms made by cross)
+__global__ void pack_arms_kernel(const float *__restrict__ xc, uint32_t *__restrict__ packed, int H, int W, int *maxlen)
+{
+	int id = blockIdx.x * blockDim.x + threadIdx.x;
+	int HW = H * W;
+	int m = 0;
+	if (id < HW) {
+		int x = id % W, y = id / W;
+		int l = x - (int)xc[id];
+		int r = (int)xc[HW + id] - x;
+		int u = y - (int)xc[2 * HW + id];
+		int d = (int)xc[3 * HW + id] - y;
+		m = max(max(l, r), max(u, d));
+		int lo = min(min(l, r), min(u, d));
+		if (lo < 0) m = 1 << 20;  // not a cross() output: force the generic kernel
+		l = min(max(l, 0), 255); r = min(max(r, 0), 255);
+		u = min(max(u, 0), 255); d = min(max(d, 0), 255);
+		packed[id] = (uint32_t)l | ((uint32_t)r << 8) | ((uint32_t)u << 16) | ((uint32_t)d << 24);
+	}
+	m = __reduce_max_sync(0xffffffffu, m);
+	if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxlen, m);
+}
+
+// ------------------------------------------------------------------ cbca, shared-memory tile
+constexpr int CB_TX = 64, CB_TY = 16, CB_DCH = 16, CB_NT = 256;
+
+template <int R>  // halo = longest arm - 1
+__global__ void __launch_bounds__(CB_NT)
+cbca_tile_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
+		 const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction)
+{
+	constexpr int TH = CB_TY + 2 * R;          // tile rows incl. halo
+	constexpr int TW = CB_TX + 2 * R;          // volume tile columns incl. halo
+	constexpr int A1W = CB_TX + CB_DCH;        // right-image arm window columns
+	__shared__ uint32_t sa0[TH][CB_TX];
+	__shared__ uint32_t sa1[TH][A1W];
+	__shared__ float sv[TH][TW + 1];
+
+	const int tid = threadIdx.x;
+	const int x0 = blockIdx.x * CB_TX, y0 = blockIdx.y * CB_TY, d0 = blockIdx.z * CB_DCH;
+	const int dn = min(CB_DCH, D - d0);
+	// column of the right image that sa1[.][0] holds: xs = x + d*direction spans
+	// [x0 + dlo, x0 + CB_TX - 1 + dhi] with (dlo,dhi) = (d0,d0+dn-1)*direction sorted
+	const int a1x0 = direction > 0 ? x0 + d0 : x0 - (d0 + CB_DCH - 1);
+
+	for (int i = tid; i < TH * CB_TX; i += CB_NT) {
+		int r = i / CB_TX, c = i % CB_TX;
+		int yy = y0 - R + r, xx = x0 + c;
+		sa0[r][c] = (yy >= 0 && yy < H && xx < W) ? a0g[yy * W + xx] : 0u;
+	}
+	for (int i = tid; i < TH * A1W; i += CB_NT) {
+		int r = i / A1W, c = i % A1W;
+		int yy = y0 - R + r, xx = a1x0 + c;
+		sa1[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? a1g[yy * W + xx] : 0u;
+	}
+
+	const int lx = tid % CB_TX;                // 0..63
+	const int ly = tid / CB_TX;                // 0..3 ; rows ly, ly+4, ly+8, ly+12
+	const int x = x0 + lx;
+	const long HW = (long)H * W;
+
+	for (int dd = 0; dd < dn; dd++) {
+		const int d = d0 + dd;
+		const float *plane = vol + (long)d * HW;
+		__syncthreads();  // previous plane consumed (and arms visible on the first pass)
+		for (int i = tid; i < TH * TW; i += CB_NT) {
+			int r = i / TW, c = i % TW;
+			int yy = y0 - R + r, xx = x0 - R + c;
+			sv[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(plane + (long)yy * W + xx) : 0.0f;
+		}
+		__syncthreads();
+		const int xs = x + d * direction;
+		const int c1 = xs - a1x0;              // column in sa1
+#pragma unroll
+		for (int k = 0; k < CB_TY / 4; k++) {
+			const int y = y0 + ly + 4 * k;
+			if (x >= W || y >= H) continue;
+			const int r = ly + 4 * k + R;      // tile row of y
+			float res;
+			if (xs < 0 || xs >= W) {
+				res = sv[r][lx + R];           // adcensus.cu:353-354 (keeps NaN)
+			} else {
+				uint32_t mc = __vminu4(sa0[r][lx], sa1[r][c1]);
+				int up = (mc >> 16) & 255, dn_ = mc >> 24;
+				float sum = 0.0f;
+				int cnt = 0;
+				for (int rr = r - up + 1; rr < r + dn_; rr++) {           // :361
+					uint32_t m = __vminu4(sa0[rr][lx], sa1[rr][c1]);
+					int lo = lx + R - (int)(m & 255) + 1;                  // :362
+					int hi = lx + R + (int)((m >> 8) & 255);               // :363 (exclusive)
+					const float *row = sv[rr];
+					for (int cc = lo; cc < hi; cc++) sum += row[cc];       // :364-369
+					cnt += hi - lo;
+				}
+				res = sum / (float)cnt;                                    // :373
+			}
+			out[(long)d * HW + (long)y * W + x] = res;
+		}
+	}
+}
+
+// ------------------------------------------------------------------ cbca, generic (any arm length)
+// Same arithmetic straight from global memory; used when an arm is longer than the
+// largest shared-memory halo or the arms are not integer cross() outputs.
+__global__ void cbca_generic_kernel(const float *__restrict__ x0c, const float *__restrict__ x1c,
+				    const float *__restrict__ vol, float *__restrict__ out,
+				    long size, int H, int W, int direction)
+{
+	long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= size) return;
+	long HW = (long)H * W;
+	int x = (int)(id % W);
+	int y = (int)((id / W) % H);
+	int d = (int)(id / HW);
+	int xs = x + d * direction;
+	if (xs < 0 || xs >= W) { out[id] = vol[id]; return; }
+	float sum = 0.0f;
+	int cnt = 0;
+	int yy_s = (int)fmaxf(x0c[2 * HW + (long)y * W + x], x1c[2 * HW + (long)y * W + xs]);
+	int yy_t = (int)fminf(x0c[3 * HW + (long)y * W + x], x1c[3 * HW + (long)y * W + xs]);
+	for (int yy = yy_s + 1; yy < yy_t; yy++) {
+		int xx_s = (int)fmaxf(x0c[(long)yy * W + x], x1c[(long)yy * W + xs] - d * direction);
+		int xx_t = (int)fminf(x0c[HW + (long)yy * W + x], x1c[HW + (long)yy * W + xs] - d * direction);
+		for (int xx = xx_s + 1; xx < xx_t; xx++) {
+			sum += __ldg(vol + (long)d * HW + (long)yy * W + xx);
+			cnt++;
+		}
+	}
+	out[id] = sum / (float)cnt;
+}
+
+template <int R>
+void launch_tile(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int direction, cudaStream_t s)
+{
+	dim3 grid(adc_div_up(W, CB_TX), adc_div_up(H, CB_TY), adc_div_up(D, CB_DCH));
+	cbca_tile_kernel<R><<<grid, CB_NT, 0, s>>>(a0, a1, vol, out, D, H, W, direction);
+}
+
+}  // namespace
+
+// ---- internal entry points shared with pipeline.cu -------------------------
+int adc_pack_arms(const float *xc, uint32_t *packed, int H, int W, int *maxlen_dev, cudaStream_t s)
+{
+	pack_arms_kernel<<<adc_div_up((long)H * W, 256), 256, 0, s>>>(xc, packed, H, W, maxlen_dev);
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+// maxlen = longest arm (distance to the exclusive end-point) of either image
+int adc_cbca_packed(const uint32_t *a0, const uint32_t *a1, const float *x0c, const float *x1c,
+		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s)
+{
+	int halo = maxlen - 1;
+	if (halo <= 1) launch_tile<1>(a0, a1, vol, out, D, H, W, direction, s);
+	else if (halo <= 4) launch_tile<4>(a0, a1, vol, out, D, H, W, direction, s);
+	else if (halo <= 8) launch_tile<8>(a0, a1, vol, out, D, H, W, direction, s);
+	else if (halo <= 13) launch_tile<13>(a0, a1, vol, out, D, H, W, direction, s);
+	else {
+		long size = (long)D * H * W;
+		cbca_generic_kernel<<<adc_div_up(size, 256), 256, 0, s>>>(x0c, x1c, vol, out, size, H, W, direction);
+	}
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+extern "C" int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1, adcensus_stream_t stream)
+{
+	if (!x0 || !out || H < 1 || W < 1) return ADCENSUS_EINVAL;
+	long n = 4L * H * W;
+	cross_kernel<<<adc_div_up(n, 256), 256, 0, adc_stream(stream)>>>(x0, out, H, W, L1, tau1);
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+extern "C" int adcensus_cbca(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+			     int D, int H, int W, int direction, adcensus_stream_t stream)
+{
+	if (!x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
+	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1)) return ADCENSUS_EINVAL;
+	cudaStream_t s = adc_stream(stream);
+	long HW = (long)H * W;
+	uint32_t *packed = nullptr;
+	int rc = adc_scratch_alloc((void **)&packed, (2 * HW + 1) * sizeof(uint32_t), s);
+	if (rc) return rc;
+	int *maxlen_dev = (int *)(packed + 2 * HW);
+	int maxlen = 0;
+	rc = (int)cudaMemsetAsync(maxlen_dev, 0, sizeof(int), s);
+	if (!rc) rc = adc_pack_arms(x0c, packed, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_pack_arms(x1c, packed + HW, H, W, maxlen_dev, s);
+	if (!rc) rc = (int)cudaMemcpyAsync(&maxlen, maxlen_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+	if (!rc) rc = (int)cudaStreamSynchronize(s);
+	if (!rc) rc = adc_cbca_packed(packed, packed + HW, x0c, x1c, vol_in, vol_out, D, H, W, direction, maxlen, s);
+	int rc2 = adc_scratch_free(packed, s);
+	return rc ? rc : rc2;
+}

@@ -1,0 +1,221 @@
+// pipeline.cu -- stereo_predict (main.lua:929-1082, arch 'fast') as one native
+// object: every device buffer is allocated once at create time, a run is a fixed
+// sequence of kernel launches on one stream (no allocation, no host sync), so a
+// batch driver can keep one pipeline per GPU / per stream busy back to back.
+//
+// Stage order, which volume is "left"/"right", the direction loop {+1,-1}, the /4
+// and the permutes follow main.lua line by line (cited inline); the kernels are
+// the ones behind the adcensus_* C ABI.
+#include <math.h>
+#include <new>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+// internal entry points of the other translation units
+int adc_pack_arms(const float *xc, uint32_t *packed, int H, int W, int *maxlen_dev, cudaStream_t s);
+int adc_cbca_packed(const uint32_t *a0, const uint32_t *a1, const float *x0c, const float *x1c,
+		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s);
+int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, int H, int W, int D,
+	     float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
+	     bool zero_out, cudaStream_t s);
+
+struct mccnn_pipeline {
+	int C, D, H, W, device;
+	mccnn_params prm;
+	long HW, V;
+	size_t bytes;
+	int launches;
+	// device buffers
+	float *vols;      // 2V: [0] left volume, [1] right volume (main.lua:946)
+	float *bufA;      // V : CBCA ping-pong / SGM transposed input
+	float *bufC;      // V : SGM accumulator (H,W,D)
+	float *x0c, *x1c; // 4HW each: cross arms (main.lua:993-996)
+	uint32_t *packed; // 2HW: packed arm lengths
+	int *maxlen;
+	float *maps;      // 8HW: disparity maps and stage outputs
+	float *gauss;     // ks*ks
+	int ks;
+	// staging for the host-buffer entry point
+	float *h_feat, *h_img, *h_disp;  // device copies: 2F, 2HW, HW
+	cudaStream_t own_stream;
+};
+
+namespace {
+
+int dev_alloc(void **p, size_t bytes, size_t *acc)
+{
+	cudaError_t e = cudaMalloc(p, bytes);
+	if (e != cudaSuccess) return (int)e;
+	*acc += bytes;
+	return 0;
+}
+
+struct DeviceGuard {
+	int prev;
+	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+	~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, int W, const mccnn_params *params, int device)
+{
+	if (!out || !params || C < 1 || D < 1 || H < 1 || W < 1) return ADCENSUS_EINVAL;
+	if (C > 128 || D > ADCENSUS_MAX_DISP) return ADCENSUS_ELIMIT;
+	if (params->cbca_i1 < 0 || params->cbca_i2 < 0 || params->sgm_i < 0 || params->border < 0 || params->border + 1 > W)
+		return ADCENSUS_EINVAL;
+	DeviceGuard g(device);
+	mccnn_pipeline *p = new (std::nothrow) mccnn_pipeline();
+	if (!p) return ADCENSUS_EINVAL;
+	memset(p, 0, sizeof(*p));
+	p->C = C; p->D = D; p->H = H; p->W = W; p->device = device;
+	p->prm = *params;
+	p->HW = (long)H * W;
+	p->V = (long)D * p->HW;
+	int rc = 0;
+	const size_t f = sizeof(float);
+	if (!rc) rc = dev_alloc((void **)&p->vols, 2 * p->V * f, &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->bufA, p->V * f, &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->bufC, p->V * f, &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->x0c, 4 * p->HW * f, &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->x1c, 4 * p->HW * f, &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->packed, 2 * p->HW * sizeof(uint32_t), &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->maxlen, sizeof(int), &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->maps, 8 * p->HW * f, &p->bytes);
+	p->ks = mccnn_gaussian(params->blur_sigma, nullptr);
+	if (!rc) rc = dev_alloc((void **)&p->gauss, (size_t)p->ks * p->ks * f, &p->bytes);
+	if (!rc) {
+		float *hk = (float *)malloc((size_t)p->ks * p->ks * f);
+		mccnn_gaussian(params->blur_sigma, hk);  // main.lua:1078 gaussian(opt.blur_sigma):cuda()
+		rc = (int)cudaMemcpy(p->gauss, hk, (size_t)p->ks * p->ks * f, cudaMemcpyHostToDevice);
+		free(hk);
+	}
+	if (rc) {
+		mccnn_pipeline_destroy(p);
+		return rc;
+	}
+	*out = p;
+	return 0;
+}
+
+extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
+{
+	if (!p) return;
+	DeviceGuard g(p->device);
+	cudaFree(p->vols); cudaFree(p->bufA); cudaFree(p->bufC); cudaFree(p->x0c); cudaFree(p->x1c);
+	cudaFree(p->packed); cudaFree(p->maxlen); cudaFree(p->maps); cudaFree(p->gauss);
+	cudaFree(p->h_feat); cudaFree(p->h_img); cudaFree(p->h_disp);
+	if (p->own_stream) cudaStreamDestroy(p->own_stream);
+	delete p;
+}
+
+extern "C" size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p) { return p ? p->bytes : 0; }
+extern "C" int mccnn_pipeline_launches_per_run(const mccnn_pipeline *p) { return p ? p->launches : 0; }
+
+#define STEP(call)                 \
+	do {                       \
+		int rc__ = (call); \
+		if (rc__) return rc__; \
+	} while (0)
+
+extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const float *featR,
+				  const float *imgL, const float *imgR, float *disp,
+				  float *volL, float *volR, adcensus_stream_t stream)
+{
+	if (!p || !featL || !featR || !imgL || !imgR || !disp) return ADCENSUS_EINVAL;
+	DeviceGuard g(p->device);
+	cudaStream_t s = adc_stream(stream);
+	const int C = p->C, D = p->D, H = p->H, W = p->W;
+	const long HW = p->HW, V = p->V;
+	const mccnn_params &o = p->prm;
+	int nl = 0;
+
+	float *volsL = p->vols, *volsR = p->vols + V;
+	STEP(mccnn_fill_nan(p->vols, (size_t)(2 * V), s)); nl += 1;                                  // main.lua:946
+	STEP(adcensus_StereoJoin(featL, featR, volsL, volsR, C, D, H, W, s)); nl += 1;               // :947
+	STEP(mccnn_fix_border(volsL, D, H, W, o.border, -1, s));                                     // :948
+	STEP(mccnn_fix_border(volsR, D, H, W, o.border, 1, s)); nl += o.border ? 2 : 0;              // :949
+
+	// cross arms: identical for both directions (main.lua:993-996 recomputes them)
+	const int maxlen = o.L1 > 2 ? o.L1 : 2;  // bound on the arm length cross() can produce
+	STEP(adcensus_cross(imgL, p->x0c, H, W, o.L1, o.tau1, s));
+	STEP(adcensus_cross(imgR, p->x1c, H, W, o.L1, o.tau1, s));
+	STEP(adc_pack_arms(p->x0c, p->packed, H, W, p->maxlen, s));
+	STEP(adc_pack_arms(p->x1c, p->packed + HW, H, W, p->maxlen, s)); nl += 4;
+
+	float *dispR = p->maps, *dispL = p->maps + HW;
+	float *final_left = nullptr;
+	float *spare = p->bufA;
+	const int directions[2] = {1, -1};                                                           // :955
+	for (int k = 0; k < 2; k++) {
+		const int direction = directions[k];
+		float *cur = direction == -1 ? volsL : volsR;                                            // :986
+		for (int i = 0; i < o.cbca_i1; i++) {                                                    // :998-1001
+			STEP(adc_cbca_packed(p->packed, p->packed + HW, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, s));
+			float *t = cur; cur = spare; spare = t; nl += 1;
+		}
+		for (int it = 0; it < o.sgm_i; it++) {                                                   // :1008-1020
+			STEP(mccnn_transpose_dhw_to_hwd(cur, spare, D, H, W, s));                            // :1008
+			STEP(adc_sgm2(imgL, imgR, spare, p->bufC, H, W, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
+				      o.sgm_q1, o.sgm_q2, direction, /*zero_out=*/true, s));                     // :1014-1016
+			STEP(mccnn_transpose_hwd_to_dhw_div4(p->bufC, cur, D, H, W, s));                     // :1017-1020
+			nl += 6;
+		}
+		for (int i = 0; i < o.cbca_i2; i++) {                                                    // :1035-1038
+			STEP(adc_cbca_packed(p->packed, p->packed + HW, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, s));
+			float *t = cur; cur = spare; spare = t; nl += 1;
+		}
+		STEP(mccnn_argmin(cur, direction == 1 ? dispR : dispL, D, (int)HW, s)); nl += 1;         // :1049-1050
+		float *dst = direction == 1 ? volR : volL;                                               // :1042-1047
+		if (dst) {
+			STEP((int)cudaMemcpyAsync(dst, cur, V * sizeof(float), cudaMemcpyDeviceToDevice, s));
+		}
+		if (direction == -1) final_left = cur;
+		// the right volume is dead after its argmin: both of its buffers may serve as spares,
+		// `spare` already points at a free one
+	}
+
+	float *m = p->maps;
+	const float *curd = dispL;                                                                   // disp[2]
+	if (o.lr_check) {                                                                            // :1054-1066
+		float *outlier = m + 2 * HW;
+		STEP(adcensus_outlier_detection(dispL, dispR, outlier, H, W, D, s));                     // :1056
+		STEP(adcensus_interpolate_occlusion(curd, outlier, m + 3 * HW, H, W, s));                // :1058
+		STEP(adcensus_interpolate_mismatch(m + 3 * HW, outlier, m + 4 * HW, H, W, s));           // :1063
+		curd = m + 4 * HW; nl += 3;
+	}
+	STEP(adcensus_subpixel_enchancement(curd, final_left, m + 5 * HW, H, W, D, s));              // :1068
+	STEP(adcensus_median2d(m + 5 * HW, m + 6 * HW, H, W, 5, s));                                 // :1073
+	STEP(adcensus_mean2d(m + 6 * HW, p->gauss, disp, H, W, p->ks, o.blur_t, s)); nl += 3;        // :1078
+	p->launches = nl;
+	return 0;
+}
+
+extern "C" int mccnn_pipeline_run_host(mccnn_pipeline *p, const float *featL_host, const float *featR_host,
+				       const float *imgL_host, const float *imgR_host, float *disp_host)
+{
+	if (!p || !featL_host || !featR_host || !imgL_host || !imgR_host || !disp_host) return ADCENSUS_EINVAL;
+	DeviceGuard g(p->device);
+	const size_t F = (size_t)p->C * p->HW * sizeof(float), I = (size_t)p->HW * sizeof(float);
+	if (!p->h_feat) {
+		int rc = 0;
+		if (!rc) rc = dev_alloc((void **)&p->h_feat, 2 * F, &p->bytes);
+		if (!rc) rc = dev_alloc((void **)&p->h_img, 2 * I, &p->bytes);
+		if (!rc) rc = dev_alloc((void **)&p->h_disp, I, &p->bytes);
+		if (!rc) rc = (int)cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+		if (rc) return rc;
+	}
+	cudaStream_t s = p->own_stream;
+	float *fL = p->h_feat, *fR = p->h_feat + (size_t)p->C * p->HW;
+	float *iL = p->h_img, *iR = p->h_img + p->HW;
+	ADC_CUDA(cudaMemcpyAsync(fL, featL_host, F, cudaMemcpyHostToDevice, s));
+	ADC_CUDA(cudaMemcpyAsync(fR, featR_host, F, cudaMemcpyHostToDevice, s));
+	ADC_CUDA(cudaMemcpyAsync(iL, imgL_host, I, cudaMemcpyHostToDevice, s));
+	ADC_CUDA(cudaMemcpyAsync(iR, imgR_host, I, cudaMemcpyHostToDevice, s));
+	STEP(mccnn_pipeline_run(p, fL, fR, iL, iR, p->h_disp, nullptr, nullptr, s));
+	ADC_CUDA(cudaMemcpyAsync(disp_host, p->h_disp, I, cudaMemcpyDeviceToHost, s));
+	ADC_CUDA(cudaStreamSynchronize(s));
+	return 0;
+}

@@ -1,0 +1,190 @@
+"""stereo_predict for the 'fast' architecture, from the tower output onwards.
+
+Two faces over the same kernels:
+
+* :func:`stereo_predict` chains the ``adcensus.*`` operator calls exactly as
+  main.lua:929-1082 does (same order, same tensors, same Lua-side fill / copy /
+  transpose / argmin steps), so it reads like the reference's own driver;
+* :class:`StereoPipeline` is the native fused object behind
+  ``mccnn_pipeline_*`` (include/adcensus_b200.h): buffers allocated once, one
+  stream, no host sync -- what bench.py and a batch driver use.
+
+Hyper-parameter presets are main.lua:70-295 copied as data.
+"""
+import ctypes
+
+import torch
+
+from . import adcensus
+
+
+class Params(ctypes.Structure):
+    """mccnn_params; field names are main.lua's option names."""
+
+    _fields_ = [
+        ("L1", ctypes.c_int),
+        ("tau1", ctypes.c_float),
+        ("cbca_i1", ctypes.c_int),
+        ("cbca_i2", ctypes.c_int),
+        ("pi1", ctypes.c_float),
+        ("pi2", ctypes.c_float),
+        ("sgm_q1", ctypes.c_float),
+        ("sgm_q2", ctypes.c_float),
+        ("alpha1", ctypes.c_float),
+        ("tau_so", ctypes.c_float),
+        ("sgm_i", ctypes.c_int),
+        ("blur_sigma", ctypes.c_double),
+        ("blur_t", ctypes.c_float),
+        ("border", ctypes.c_int),
+        ("lr_check", ctypes.c_int),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# (dataset, arch) -> stereo-method options, main.lua:70-295.  `border` = (window-1)/2 of the
+# feature tower (main.lua:382-391, 923): 4 conv3x3 layers -> 4 (mb: 5 layers -> 5).
+PRESETS = {
+    ("kitti", "slow"): dict(L1=5, tau1=0.13, cbca_i1=2, cbca_i2=0, pi1=1.32, pi2=24.25, sgm_q1=3, sgm_q2=2,
+                            alpha1=2, tau_so=0.08, blur_sigma=5.99, blur_t=6, border=4, lr_check=1),
+    ("kitti2015", "slow"): dict(L1=5, tau1=0.03, cbca_i1=2, cbca_i2=4, pi1=2.3, pi2=24.25, sgm_q1=3, sgm_q2=2,
+                                alpha1=1.75, tau_so=0.08, blur_sigma=5.99, blur_t=5, border=4, lr_check=1),
+    ("mb", "slow"): dict(L1=14, tau1=0.02, cbca_i1=2, cbca_i2=16, pi1=1.3, pi2=13.9, sgm_q1=4.5, sgm_q2=2,
+                         alpha1=2.75, tau_so=0.13, blur_sigma=1.67, blur_t=2, border=5, lr_check=0),
+    ("kitti", "fast"): dict(L1=0, tau1=0, cbca_i1=0, cbca_i2=0, pi1=4, pi2=55.72, sgm_q1=3, sgm_q2=2.5,
+                            alpha1=1.5, tau_so=0.02, blur_sigma=7.74, blur_t=5, border=4, lr_check=1),
+    ("kitti2015", "fast"): dict(L1=0, tau1=0, cbca_i1=0, cbca_i2=0, pi1=2.3, pi2=18.38, sgm_q1=3, sgm_q2=2,
+                                alpha1=1.25, tau_so=0.08, blur_sigma=4.64, blur_t=5, border=4, lr_check=1),
+    ("mb", "fast"): dict(L1=0, tau1=0, cbca_i1=0, cbca_i2=0, pi1=2.3, pi2=24.3, sgm_q1=4, sgm_q2=2,
+                         alpha1=1.5, tau_so=0.08, blur_sigma=6, blur_t=2, border=5, lr_check=0),
+    # BASELINE.json config 3 ("KITTI accurate: CBCA x4 + SGM"): kitti slow post-processing with
+    # cbca_i1 = cbca_i2 = 2
+    ("kitti", "accurate_cbca4"): dict(L1=5, tau1=0.13, cbca_i1=2, cbca_i2=2, pi1=1.32, pi2=24.25, sgm_q1=3,
+                                      sgm_q2=2, alpha1=2, tau_so=0.08, blur_sigma=5.99, blur_t=6, border=4,
+                                      lr_check=1),
+}
+
+
+def make_params(dataset="kitti", arch="fast", **overrides):
+    d = dict(PRESETS[(dataset, arch)])
+    d.setdefault("sgm_i", 1)
+    d.update(overrides)
+    return Params(**d)
+
+
+def stereo_predict(x_batch, features, opt, disp_max, want_vols=False):
+    """main.lua:929-1082 (arch == 'fast') through the adcensus.* operators.
+
+    x_batch  (2,1,H,W) standardised images (left, right); features (2,C,H,W) the tower
+    output (unit-norm); opt a :class:`Params`.  Returns disp (1,1,H,W) [, left vol, right vol].
+    """
+    assert x_batch.is_cuda and features.is_cuda
+    H, W = x_batch.size(2), x_batch.size(3)
+    dev = x_batch.device
+    vols = torch.empty((2, disp_max, H, W), device=dev, dtype=torch.float32)
+    adcensus.fill_nan(vols)                                                       # :946
+    adcensus.StereoJoin(features[0:1], features[1:2], vols[0:1], vols[1:2])       # :947
+    adcensus.fix_border(vols[0:1], opt.border, -1)                                # :948
+    adcensus.fix_border(vols[1:2], opt.border, 1)                                 # :949
+
+    disp = {}
+    out_vols = {}
+    vol = None
+    for direction in (1, -1):                                                     # :955
+        vol = vols[0:1] if direction == -1 else vols[1:2]                         # :986
+        x0c = torch.empty((1, 4, H, W), device=dev, dtype=torch.float32)          # :993-996
+        x1c = torch.empty((1, 4, H, W), device=dev, dtype=torch.float32)
+        adcensus.cross(x_batch[0], x0c, opt.L1, opt.tau1)
+        adcensus.cross(x_batch[1], x1c, opt.L1, opt.tau1)
+        tmp_cbca = torch.empty_like(vol)
+        for _ in range(opt.cbca_i1):                                              # :998-1001
+            adcensus.cbca(x0c, x1c, vol, tmp_cbca, direction)
+            vol.copy_(tmp_cbca)
+        volt = adcensus.transpose_dhw_to_hwd(vol)                                 # :1008
+        out = torch.empty_like(volt)
+        tmp = torch.empty((W, disp_max), device=dev, dtype=torch.float32)         # :1012
+        for _ in range(opt.sgm_i):
+            out.zero_()                                                           # :1014
+            adcensus.sgm2(x_batch[0], x_batch[1], volt, out, tmp, opt.pi1, opt.pi2, opt.tau_so, opt.alpha1,
+                          opt.sgm_q1, opt.sgm_q2, direction)                      # :1015
+            volt.copy_(out).div_(4)                                               # :1017
+        vol.copy_(adcensus.transpose_hwd_to_dhw_div4(out))                        # :1019-1020
+        for _ in range(opt.cbca_i2):                                              # :1035-1038
+            adcensus.cbca(x0c, x1c, vol, tmp_cbca, direction)
+            vol.copy_(tmp_cbca)
+        if want_vols:
+            out_vols[direction] = vol.clone()                                     # :1042-1047
+        disp[1 if direction == 1 else 2] = adcensus.argmin(vol)                   # :1049-1050
+
+    d = disp[2]
+    if opt.lr_check:                                                              # :1054-1066
+        outlier = torch.zeros_like(d)
+        adcensus.outlier_detection(disp[2], disp[1], outlier, disp_max)
+        d = adcensus.interpolate_occlusion(d, outlier)
+        d = adcensus.interpolate_mismatch(d, outlier)
+    d = adcensus.subpixel_enchancement(d, vol, disp_max)                          # :1068 (left volume)
+    d = adcensus.median2d(d, 5)                                                   # :1073
+    d = adcensus.mean2d(d, adcensus.gaussian(opt.blur_sigma).to(dev), opt.blur_t)  # :1078
+    if want_vols:
+        return d, out_vols[-1], out_vols[1]
+    return d
+
+
+class StereoPipeline:
+    """Native fused stereo_predict (mccnn_pipeline_*): buffers allocated once per (C,D,H,W)."""
+
+    def __init__(self, C, D, H, W, params, device=0):
+        self.C, self.D, self.H, self.W = C, D, H, W
+        self.params = params
+        self.device = int(device)
+        self._h = ctypes.c_void_p()
+        rc = adcensus.lib().mccnn_pipeline_create(ctypes.byref(self._h), C, D, H, W, ctypes.byref(params), self.device)
+        adcensus._check(rc, "mccnn_pipeline_create")
+
+    def close(self):
+        if self._h:
+            adcensus.lib().mccnn_pipeline_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_bytes(self):
+        return adcensus.lib().mccnn_pipeline_device_bytes(self._h)
+
+    @property
+    def launches_per_run(self):
+        return adcensus.lib().mccnn_pipeline_launches_per_run(self._h)
+
+    def run(self, featL, featR, imgL, imgR, disp=None, volL=None, volR=None):
+        """Device tensors in, device disparity map out; asynchronous on torch's current stream."""
+        n = "mccnn_pipeline_run"
+        if disp is None:
+            disp = torch.empty((self.H, self.W), device=featL.device, dtype=torch.float32)
+        vp = lambda t: adcensus._t(t, 0, n) if t is not None else ctypes.c_void_p(0)
+        with torch.cuda.device(featL.device):
+            rc = adcensus.lib().mccnn_pipeline_run(self._h, adcensus._t(featL, 1, n), adcensus._t(featR, 2, n),
+                                                   adcensus._t(imgL, 3, n), adcensus._t(imgR, 4, n),
+                                                   adcensus._t(disp, 5, n), vp(volL), vp(volR),
+                                                   adcensus._stream(featL))
+        adcensus._check(rc, n)
+        return disp
+
+    def run_host(self, featL, featR, imgL, imgR, disp=None):
+        """Host (CPU, ideally pinned) float32 tensors in and out; synchronous.  This is the call
+        a non-CUDA host (the Lua/FFI side) makes: H2D + pipeline + D2H inside."""
+        n = "mccnn_pipeline_run_host"
+        for t in (featL, featR, imgL, imgR):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise adcensus.AdcensusError("%s: contiguous host float tensors expected" % n)
+        if disp is None:
+            disp = torch.empty((self.H, self.W), dtype=torch.float32)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        rc = adcensus.lib().mccnn_pipeline_run_host(self._h, p(featL), p(featR), p(imgL), p(imgR), p(disp))
+        adcensus._check(rc, n)
+        return disp

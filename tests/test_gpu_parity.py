@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, the
+committed golden fixtures (outputs of the reference's own kernels) and, when
+oracle/_ref/libadcensus_ref.so travelled to the box, the reference itself live.
+
+Bar (BASELINE.json north_star): bit-exact for index / label work; our kernels keep
+the reference's fp32 operation order, so the float volumes are required to be
+bit-identical too (NaN positions included), which is stricter than the 1e-4 the
+north star allows.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import mccnn_b200  # noqa: E402,F401
+from mccnn_b200 import adcensus, pipeline, synth  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev())
+
+
+def same(a, b, what=""):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b
+    a, b = a.reshape(b.shape), b
+    if not np.array_equal(a, b, equal_nan=True):
+        bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+        idx = np.argwhere(bad)[:5]
+        raise AssertionError("%s: %d / %d elements differ, first %s: got %s want %s" % (
+            what, bad.sum(), bad.size, idx.tolist(), a[bad][:5], b[bad][:5]))
+
+
+SIZES = [
+    # H, W, C, D
+    (64, 128, 64, 16),   # BASELINE config 1
+    (7, 33, 5, 9),       # ragged, tiny
+    (19, 150, 64, 70),   # D = 70 chunking, W not a multiple of anything
+    (5, 300, 16, 228),   # D = 228, two disparity chunks
+    (3, 40, 128, 33),    # C at the reference limit (adcensus.cu:1460)
+]
+
+
+@pytest.mark.parametrize("H,W,C,D", SIZES)
+def test_stereo_join(oracle, H, W, C, D):
+    p = synth.make_pair(H, W, C, D, seed=H + W)
+    wantL, wantR = oracle.stereo_join(p["featL"], p["featR"], D)
+    outL = torch.full((1, D, H, W), float("nan"), device=dev())
+    outR = torch.full((1, D, H, W), float("nan"), device=dev())
+    adcensus.StereoJoin(cu(p["featL"])[None], cu(p["featR"])[None], outL, outR)
+    same(outL, wantL, "StereoJoin left")
+    same(outR, wantR, "StereoJoin right")
+    # shift convention: outR[d, y, x-d] == outL[d, y, x]  (adcensus.cu:1472-1473)
+    oL, oR = outL[0].cpu().numpy(), outR[0].cpu().numpy()
+    for d in range(0, D, max(1, D // 5)):
+        if d < W:
+            assert np.array_equal(oL[d, :, d:], oR[d, :, :W - d])
+
+
+def test_stereo_join_untouched_entries(oracle):
+    """entries with x - d < 0 are not written (caller pre-fills, main.lua:946)"""
+    H, W, C, D = 4, 50, 8, 20
+    p = synth.make_pair(H, W, C, D, seed=3)
+    outL = torch.full((1, D, H, W), 7.0, device=dev())
+    outR = torch.full((1, D, H, W), 9.0, device=dev())
+    adcensus.StereoJoin(cu(p["featL"])[None], cu(p["featR"])[None], outL, outR)
+    oL, oR = outL[0].cpu().numpy(), outR[0].cpu().numpy()
+    for d in range(D):
+        assert (oL[d, :, :d] == 7.0).all()
+        assert (oR[d, :, W - d:] == 9.0).all()
+
+
+@pytest.mark.parametrize("L1,tau1", [(0, 0.0), (5, 0.13), (14, 0.02), (3, 10.0), (30, 100.0)])
+def test_cross(oracle, L1, tau1):
+    H, W = 37, 61
+    p = synth.make_pair(H, W, 2, 4, seed=L1)
+    out = torch.empty((1, 4, H, W), device=dev())
+    adcensus.cross(cu(p["imgL"])[None], out, L1, tau1)
+    same(out, oracle.cross(p["imgL"], L1, tau1), "cross")
+
+
+@pytest.mark.parametrize("L1,tau1,direction", [(5, 0.13, -1), (5, 0.13, 1), (14, 0.2, -1), (2, 0.5, 1),
+                                               (9, 5.0, -1), (20, 100.0, 1), (0, 0.0, -1)])
+def test_cbca(oracle, L1, tau1, direction):
+    H, W, C, D = 41, 83, 4, 21
+    p = synth.make_pair(H, W, C, D, seed=7)
+    volL, volR = oracle.stereo_join(p["featL"], p["featR"], D)
+    vol = volL if direction == -1 else volR
+    x0c = oracle.cross(p["imgL"], L1, tau1)
+    x1c = oracle.cross(p["imgR"], L1, tau1)
+    want = oracle.cbca(x0c, x1c, vol, direction)
+    out = torch.empty((1, D, H, W), device=dev())
+    adcensus.cbca(cu(x0c)[None], cu(x1c)[None], cu(vol)[None], out, direction)
+    same(out, want, "cbca")
+
+
+@pytest.mark.parametrize("H,W,D,direction", [(9, 31, 7, -1), (9, 31, 7, 1), (12, 40, 33, -1), (6, 50, 70, 1),
+                                             (5, 260, 228, -1), (4, 300, 300, 1), (8, 20, 64, -1)])
+def test_sgm2(oracle, H, W, D, direction):
+    p = synth.make_pair(H, W, 4, D, seed=D)
+    volL, volR = oracle.stereo_join(p["featL"], p["featR"], D)
+    vol = oracle.transpose_dhw_to_hwd(volL if direction == -1 else volR)
+    args = (1.32, 24.25, 0.08, 2.0, 3.0, 2.0, direction)
+    want = oracle.sgm2(p["imgL"], p["imgR"], vol, *args)
+    out = torch.zeros((1, H, W, D), device=dev())
+    tmp = torch.empty((W, D), device=dev())
+    adcensus.sgm2(cu(p["imgL"])[None], cu(p["imgR"])[None], cu(vol)[None], out, tmp, *args)
+    same(out, want, "sgm2")
+    # accumulation into a non-zero output (out += val, adcensus.cu:569,616)
+    init = np.random.default_rng(0).standard_normal((H, W, D)).astype(np.float32)
+    want2 = oracle.sgm2(p["imgL"], p["imgR"], vol, *args, out=init.copy())
+    out2 = cu(init)[None].clone()
+    adcensus.sgm2(cu(p["imgL"])[None], cu(p["imgR"])[None], cu(vol)[None], out2, None, *args)
+    same(out2, want2, "sgm2 accumulate")
+
+
+def test_transposes_argmin(oracle):
+    D, H, W = 13, 17, 29
+    rng = np.random.default_rng(5)
+    vol = rng.standard_normal((D, H, W)).astype(np.float32)
+    vol[rng.random((D, H, W)) < 0.1] = np.nan
+    vol[0] = np.abs(vol[0]) + 5  # d = 0 always valid
+    vol[0][np.isnan(vol[0])] = 1.0
+    t = adcensus.transpose_dhw_to_hwd(cu(vol)[None])
+    same(t, oracle.transpose_dhw_to_hwd(vol), "transpose")
+    back = adcensus.transpose_hwd_to_dhw_div4(t)
+    same(back, vol / 4, "transpose back /4")
+    am = adcensus.argmin(cu(vol)[None])
+    same(am, oracle.spatial_argmin(vol) - 1, "argmin")
+    out = torch.empty((1, 1, H, W), device=dev())
+    adcensus.spatial_argmin(cu(vol)[None], out)
+    same(out, oracle.spatial_argmin(vol), "spatial_argmin")
+    # ties -> first index
+    tie = np.zeros((4, 3, 5), np.float32)
+    same(adcensus.argmin(cu(tie)[None]), np.zeros((3, 5), np.float32), "argmin ties")
+
+
+def test_fill_fix_border(oracle):
+    D, H, W = 5, 6, 23
+    v = torch.empty((1, D, H, W), device=dev())
+    adcensus.fill_nan(v)
+    assert torch.isnan(v).all()
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((D, H, W)).astype(np.float32)
+    for n, direction in [(4, -1), (4, 1), (5, 1), (1, -1)]:
+        t = cu(a)[None].clone()
+        adcensus.fix_border(t, n, direction)
+        same(t, oracle.fix_border(a.copy(), n, direction), "fix_border")
+    # odd element counts / unaligned starts for the float4 body of fill_nan
+    buf = torch.zeros(1003, device=dev())
+    adcensus.fill_nan(buf[1:1000])
+    assert torch.isnan(buf[1:1000]).all() and buf[0] == 0 and (buf[1000:] == 0).all()
+
+
+def _post_inputs(oracle, H=45, W=97, D=24, seed=2):
+    p = synth.make_pair(H, W, 8, D, seed=seed)
+    opt = pipeline.make_params("kitti", "slow")
+    volL, volR = oracle.stereo_join(p["featL"], p["featR"], D)
+    dL = oracle.spatial_argmin(volL) - 1
+    dR = oracle.spatial_argmin(volR) - 1
+    # perturb so that occlusion and mismatch labels both occur
+    rng = np.random.default_rng(seed)
+    m = rng.random((H, W)) < 0.15
+    dL[m] = rng.integers(0, D, size=m.sum())
+    return p, opt, volL, dL, dR
+
+
+def test_post_chain(oracle):
+    H, W, D = 45, 97, 24
+    p, opt, volL, dL, dR = _post_inputs(oracle, H, W, D)
+    want_out = oracle.outlier_detection(dL, dR, D)
+    assert set(np.unique(want_out)) == {0.0, 1.0, 2.0}
+    outlier = torch.zeros((1, 1, H, W), device=dev())
+    adcensus.outlier_detection(cu(dL)[None, None], cu(dR)[None, None], outlier, D)
+    same(outlier, want_out, "outlier_detection")
+    occ = adcensus.interpolate_occlusion(cu(dL)[None, None], outlier)
+    want_occ = oracle.interpolate_occlusion(dL, want_out)
+    same(occ, want_occ, "interpolate_occlusion")
+    mis = adcensus.interpolate_mismatch(occ, outlier)
+    want_mis = oracle.interpolate_mismatch(want_occ, want_out)
+    same(mis, want_mis, "interpolate_mismatch")
+    sub = adcensus.subpixel_enchancement(mis, cu(volL)[None], D)
+    want_sub = oracle.subpixel_enchancement(want_mis, volL, D)
+    same(sub, want_sub, "subpixel_enchancement")
+    for k in (1, 3, 5, 7, 11):
+        same(adcensus.median2d(sub, k), oracle.median2d(want_sub, k), "median2d k=%d" % k)
+    med = oracle.median2d(want_sub, 5)
+    for sigma, t in [(1.2, 2.0), (5.99, 6.0), (0.4, 100.0)]:
+        kern = oracle.gaussian(sigma)
+        same(adcensus.gaussian(sigma), kern, "gaussian")
+        got = adcensus.mean2d(cu(med)[None, None], cu(kern), t)
+        same(got, oracle.mean2d(med, kern, t), "mean2d sigma=%g" % sigma)
+
+
+def test_normalize_ad_census(oracle):
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((2, 7, 11, 19)).astype(np.float32)
+    want, wnorm = oracle.normalize_forward(x)
+    norm = torch.empty((2, 1, 11, 19), device=dev())
+    out = torch.empty((2, 7, 11, 19), device=dev())
+    adcensus.Normalize_forward(cu(x), norm, out)
+    same(out, want, "Normalize_forward")
+    same(norm, wnorm, "Normalize_forward norm")
+    a = rng.standard_normal((1, 1, 15, 27)).astype(np.float32)
+    b = rng.standard_normal((1, 1, 15, 27)).astype(np.float32)
+    for direction in (-1, 1):
+        o = torch.empty((1, 6, 15, 27), device=dev())
+        adcensus.ad(cu(a), cu(b), o, direction)
+        same(o, oracle.ad(a[0, 0], b[0, 0], 6, direction), "ad")
+        adcensus.census(cu(a), cu(b), o, direction)
+        same(o, oracle.census(a[0], b[0], 6, direction), "census")
+
+
+PIPE_CASES = [
+    (64, 128, 64, 16, ("kitti", "fast"), {}),
+    (64, 128, 64, 16, ("kitti", "slow"), {}),
+    (40, 90, 16, 20, ("kitti2015", "slow"), dict(cbca_i2=3)),
+    (40, 90, 16, 20, ("mb", "slow"), dict(cbca_i2=2)),
+    (33, 70, 8, 12, ("kitti", "accurate_cbca4"), {}),
+]
+
+
+@pytest.mark.parametrize("H,W,C,D,preset,over", PIPE_CASES)
+def test_pipeline_vs_oracle(oracle, H, W, C, D, preset, over):
+    opt = pipeline.make_params(*preset, **over)
+    p = synth.make_pair(H, W, C, D, seed=H * 3 + D)
+    want, wL, wR = oracle.stereo_predict(p["featL"], p["featR"], p["imgL"], p["imgR"], D,
+                                         oracle.Params(**opt.as_dict()), want_vols=True)
+    x_batch = cu(np.stack([p["imgL"], p["imgR"]])[:, None])
+    feats = cu(np.stack([p["featL"], p["featR"]]))
+    # (a) operator by operator, as main.lua chains them
+    d, vL, vR = pipeline.stereo_predict(x_batch, feats, opt, D, want_vols=True)
+    same(vL, wL, "left.bin (op chain)")
+    same(vR, wR, "right.bin (op chain)")
+    same(d, want, "disp.bin (op chain)")
+    # (b) the fused native pipeline
+    sp = pipeline.StereoPipeline(C, D, H, W, opt)
+    volL = torch.empty((D, H, W), device=dev())
+    volR = torch.empty((D, H, W), device=dev())
+    disp = sp.run(feats[0], feats[1], x_batch[0, 0], x_batch[1, 0], volL=volL, volR=volR)
+    same(volL, wL, "left.bin (fused)")
+    same(volR, wR, "right.bin (fused)")
+    same(disp, want, "disp.bin (fused)")
+    assert sp.launches_per_run > 0
+    # (c) host-buffer entry point
+    h = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    disp_h = sp.run_host(h(p["featL"]), h(p["featR"]), h(p["imgL"]), h(p["imgR"]))
+    same(disp_h, want, "disp.bin (host call)")
+    sp.close()
+
+
+def test_against_golden(golden_dir):
+    files = sorted(glob.glob(os.path.join(golden_dir, "pipe_*.npz")))
+    if not files:
+        pytest.skip("no golden fixtures committed yet")
+    for f in files:
+        g = np.load(f)
+        H, W, C, D = [int(v) for v in g["meta"]]
+        opt = pipeline.Params(**{k: (float(v) if k in ("tau1", "pi1", "pi2", "sgm_q1", "sgm_q2", "alpha1", "tau_so",
+                                                        "blur_sigma", "blur_t") else int(v))
+                                 for k, v in zip(g["opt_names"], g["opt_values"])})
+        x_batch = cu(np.stack([g["imgL"], g["imgR"]])[:, None])
+        feats = cu(np.stack([g["featL"], g["featR"]]))
+        sp = pipeline.StereoPipeline(C, D, H, W, opt)
+        volL = torch.empty((D, H, W), device=dev())
+        disp = sp.run(feats[0], feats[1], x_batch[0, 0], x_batch[1, 0], volL=volL)
+        same(disp, g["disp"][0, 0], os.path.basename(f) + " disp")
+        outL = torch.full((1, D, H, W), float("nan"), device=dev())
+        outR = torch.full((1, D, H, W), float("nan"), device=dev())
+        adcensus.StereoJoin(feats[0:1], feats[1:2], outL, outR)
+        same(outL, g["sj_left"], os.path.basename(f) + " StereoJoin")
+        sp.close()
+
+
+def test_against_live_reference():
+    """the reference's own kernels (adcensus.cu compiled unmodified) on the same box"""
+    from oracle import refdriver
+
+    if not os.path.exists(refdriver.REF_LIB):
+        pytest.skip("oracle/_ref/libadcensus_ref.so not present")
+    shim = refdriver.ShimLibrary(refdriver.REF_LIB)
+    for (H, W, C, D, preset, over) in [(48, 100, 32, 24, ("kitti", "slow"), dict(cbca_i2=2)),
+                                       (30, 140, 64, 70, ("kitti", "fast"), {})]:
+        opt = pipeline.make_params(*preset, **over)
+        p = synth.make_pair(H, W, C, D, seed=77)
+        x_batch = cu(np.stack([p["imgL"], p["imgR"]])[:, None])
+        feats = cu(np.stack([p["featL"], p["featR"]]))
+        want, wL, wR = refdriver.stereo_predict(shim, x_batch, feats, opt, D, want_vols=True)
+        sp = pipeline.StereoPipeline(C, D, H, W, opt)
+        volL = torch.empty((D, H, W), device=dev())
+        volR = torch.empty((D, H, W), device=dev())
+        disp = sp.run(feats[0], feats[1], x_batch[0, 0], x_batch[1, 0], volL=volL, volR=volR)
+        same(volL, wL, "left.bin vs reference")
+        same(volR, wR, "right.bin vs reference")
+        same(disp, want, "disp.bin vs reference")
+        sp.close()
+
+
+def test_error_behaviour():
+    """wrong tensor types raise like luaT_checkudata; limits are rejected, not overflowed"""
+    with pytest.raises(adcensus.AdcensusError):
+        adcensus.cross(torch.zeros(1, 4, 4), torch.zeros(1, 4, 4, 4), 5, 0.1)  # CPU tensors
+    a = torch.zeros((1, 129, 2, 8), device=dev())
+    o = torch.zeros((1, 4, 2, 8), device=dev())
+    with pytest.raises(adcensus.AdcensusError):
+        adcensus.StereoJoin(a, a, o, o)  # C > 128 (adcensus.cu:1460)
+    with pytest.raises(adcensus.AdcensusError):
+        adcensus.median2d(torch.zeros((1, 1, 4, 4), device=dev()), 13)  # > 11 (adcensus.cu:1602)
