@@ -144,7 +144,7 @@ def stereo_predict(shim, x_batch, features, opt, disp_max, want_vols=False, stag
             call("cbca", x0c, x1c, vol, tmp_cbca, direction)
             vol.copy_(tmp_cbca)
         rec("cbca1_" + tag, vol)
-        volt = vol.transpose(1, 2).transpose(2, 3).clone()                                  # :1008
+        volt = vol.transpose(1, 2).transpose(2, 3).clone(memory_format=torch.contiguous_format)                                  # :1008
         out = torch.empty_like(volt)
         tmp = torch.empty((volt.size(2), volt.size(3)), device=dev, dtype=torch.float32)    # :1012
         for _ in range(opt.sgm_i):
