@@ -72,12 +72,212 @@ __global__ void pack_arms_kernel(const float *__restrict__ xc, uint32_t *__restr
 	if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxlen, m);
 }
 
-// ------------------------------------------------------------------ cbca, shared-memory tile
+// ------------------------------------------------------------------ cbca, fixed-window register stencil
+// (arms up to 5 pixels: every KITTI preset, main.lua:86-113,207-262)
+//
+// A thread owns 4 consecutive x times 2 consecutive y outputs of one disparity plane and walks the
+// 2R+2 tile rows that cover both supports once: per row it loads the 4+2R window columns
+// (LDS.128) and the 4 combined arm words into registers and then issues, for every output and
+// every window slot, one compare (slot inside the run AND row inside the vertical arm) and one
+// predicated FADD.  No data-dependent loop, no divergence; the order of additions per output is
+// still rows ascending, columns ascending, so results stay bit-identical to adcensus.cu:361-370.
+constexpr int CW_TX = 128, CW_TY = 16, CW_DCH = 16, CW_NT = 256;
+
+template <int R>
+struct CWCfg {
+	static constexpr int TH = CW_TY + 2 * R;
+	static constexpr int NV = (4 + 2 * R + 3) / 4;              // float4 loads per window row
+	static constexpr int TWP = ((CW_TX + 2 * R + 3) / 4) * 4 + ((NV * 4 > 4 + 2 * R) ? 4 : 0);
+	static constexpr int A1W = CW_TX + CW_DCH;
+	static constexpr int SMEM = (TH * CW_TX + TH * A1W + TH * CW_TX + TH * TWP) * 4;
+};
+
+// One output, one support row: q = row inside the vertical arm; then for every window slot one
+// compare (slot inside the horizontal run, ANDed with q) and one predicated add.f32, in column
+// order.  Inline PTX because nvcc otherwise lowers `if (p) acc += w` to FADD + FSEL.
+template <int R>
+__device__ __forceinline__ void row_taps(float &acc, int &cnt, const float *w, int L, int Rr, int LR, int va, int vthr);
+
+template <>
+__device__ __forceinline__ void row_taps<4>(float &acc, int &cnt, const float *w, int L, int Rr, int LR, int va, int vthr)
+{
+	asm("{\n\t.reg .pred q, p;\n\t"
+	    "setp.gt.s32 q, %13, %14;\n\t"
+	    "setp.gt.and.s32 p, %11, 4, q;\n\t@p add.f32 %0, %0, %2;\n\t"
+	    "setp.gt.and.s32 p, %11, 3, q;\n\t@p add.f32 %0, %0, %3;\n\t"
+	    "setp.gt.and.s32 p, %11, 2, q;\n\t@p add.f32 %0, %0, %4;\n\t"
+	    "setp.gt.and.s32 p, %11, 1, q;\n\t@p add.f32 %0, %0, %5;\n\t"
+	    "@q add.f32 %0, %0, %6;\n\t"
+	    "setp.gt.and.s32 p, %12, 1, q;\n\t@p add.f32 %0, %0, %7;\n\t"
+	    "setp.gt.and.s32 p, %12, 2, q;\n\t@p add.f32 %0, %0, %8;\n\t"
+	    "setp.gt.and.s32 p, %12, 3, q;\n\t@p add.f32 %0, %0, %9;\n\t"
+	    "setp.gt.and.s32 p, %12, 4, q;\n\t@p add.f32 %0, %0, %10;\n\t"
+	    "@q add.s32 %1, %1, %15;\n\t}"
+	    : "+f"(acc), "+r"(cnt)
+	    : "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]), "f"(w[4]), "f"(w[5]), "f"(w[6]), "f"(w[7]), "f"(w[8]),
+	      "r"(L), "r"(Rr), "r"(va), "r"(vthr), "r"(LR));
+}
+
+template <>
+__device__ __forceinline__ void row_taps<1>(float &acc, int &cnt, const float *w, int L, int Rr, int LR, int va, int vthr)
+{
+	asm("{\n\t.reg .pred q, p;\n\t"
+	    "setp.gt.s32 q, %7, %8;\n\t"
+	    "setp.gt.and.s32 p, %5, 1, q;\n\t@p add.f32 %0, %0, %2;\n\t"
+	    "@q add.f32 %0, %0, %3;\n\t"
+	    "setp.gt.and.s32 p, %6, 1, q;\n\t@p add.f32 %0, %0, %4;\n\t"
+	    "@q add.s32 %1, %1, %9;\n\t}"
+	    : "+f"(acc), "+r"(cnt)
+	    : "f"(w[0]), "f"(w[1]), "f"(w[2]), "r"(L), "r"(Rr), "r"(va), "r"(vthr), "r"(LR));
+}
+
+template <int R>
+__global__ void __launch_bounds__(CW_NT)
+cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
+		const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction)
+{
+	using Cfg = CWCfg<R>;
+	constexpr int TH = Cfg::TH, TWP = Cfg::TWP, A1W = Cfg::A1W, NV = Cfg::NV;
+	extern __shared__ __align__(16) uint32_t cw_smem[];
+	uint32_t *sa0 = cw_smem;                       // [TH][CW_TX]  left-image arms of the tile
+	uint32_t *sa1 = sa0 + TH * CW_TX;              // [TH][A1W]    right-image arms, shifted window
+	uint32_t *scomb = sa1 + TH * A1W;              // [TH][CW_TX]  vmin4 of both for the current d
+	float *sv = reinterpret_cast<float *>(scomb + TH * CW_TX);  // [TH][TWP] volume plane tile + halo
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int x0 = blockIdx.x * CW_TX, y0 = blockIdx.y * CW_TY, d0 = blockIdx.z * CW_DCH;
+	const int dn = min(CW_DCH, D - d0);
+	const int a1x0 = direction > 0 ? x0 + d0 : x0 - (d0 + CW_DCH - 1);
+	const long HW = (long)H * W;
+
+	const int cx = 4 * lane;                       // first of this thread's 4 tile columns
+	const int ry = 2 * warp;                       // first of this thread's 2 output rows (tile-relative)
+	constexpr int NW = CW_NT / 32;
+
+	// packed arms: one warp per tile row, lanes along x (no index division anywhere)
+	for (int r = warp; r < TH; r += NW) {
+		const int yy = y0 - R + r;
+		const bool rowok = yy >= 0 && yy < H;
+#pragma unroll
+		for (int m = 0; m < CW_TX / 32; m++) {
+			int c = lane + 32 * m, xx = x0 + c;
+			sa0[r * CW_TX + c] = (rowok && xx < W) ? __ldg(a0g + yy * W + xx) : 0u;
+		}
+#pragma unroll
+		for (int m = 0; m < (A1W + 31) / 32; m++) {
+			int c = lane + 32 * m, xx = a1x0 + c;
+			if (c < A1W) sa1[r * A1W + c] = (rowok && xx >= 0 && xx < W) ? __ldg(a1g + yy * W + xx) : 0u;
+		}
+	}
+
+	for (int dd = 0; dd < dn; dd++) {
+		const int d = d0 + dd;
+		const float *plane = vol + (long)d * HW;
+		const int off = (x0 + d * direction) - a1x0;   // sa1 column of tile column 0
+		__syncthreads();                               // previous plane consumed; arms visible
+		// volume plane tile (+halo): cp.async, 4-byte granules (rows of W floats are only 4-byte
+		// aligned), zero-filled outside the image
+		for (int r = warp; r < TH; r += NW) {
+			const int yy = y0 - R + r;
+			const bool rowok = yy >= 0 && yy < H;
+			const float *grow = plane + (long)(rowok ? yy : 0) * W;
+#pragma unroll
+			for (int m = 0; m < (TWP + 31) / 32; m++) {
+				const int c = lane + 32 * m, xx = x0 - R + c;
+				if (c < TWP) {
+					const bool ok = rowok && xx >= 0 && xx < W;
+					const unsigned dst = (unsigned)__cvta_generic_to_shared(sv + r * TWP + c);
+					const int nbytes = ok ? 4 : 0;
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(grow + (ok ? xx : 0)), "r"(nbytes));
+				}
+			}
+		}
+		asm volatile("cp.async.commit_group;");
+		// combined arms of this disparity: this thread's 4 columns of every NW-th row
+		for (int r = warp; r < TH; r += NW) {
+			uint4 a = *reinterpret_cast<const uint4 *>(sa0 + r * CW_TX + cx);
+			const uint32_t *b = sa1 + r * A1W + cx + off;
+			uint4 c;
+			c.x = __vminu4(a.x, b[0]);
+			c.y = __vminu4(a.y, b[1]);
+			c.z = __vminu4(a.z, b[2]);
+			c.w = __vminu4(a.w, b[3]);
+			*reinterpret_cast<uint4 *>(scomb + r * CW_TX + cx) = c;
+		}
+		asm volatile("cp.async.wait_group 0;");
+		__syncthreads();
+
+		int U[2][4], Dn[2][4];
+#pragma unroll
+		for (int oy = 0; oy < 2; oy++) {
+			uint4 cc = *reinterpret_cast<const uint4 *>(scomb + (ry + oy + R) * CW_TX + cx);
+			uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				U[oy][j] = (c4[j] >> 16) & 255;
+				Dn[oy][j] = c4[j] >> 24;
+			}
+		}
+		float acc[2][4];
+		int cnt[2][4];
+#pragma unroll
+		for (int oy = 0; oy < 2; oy++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) { acc[oy][j] = 0.0f; cnt[oy][j] = 0; }
+
+#pragma unroll
+		for (int ri = 0; ri < 2 * R + 2; ri++) {
+			float w[NV * 4];
+			const float *wrow = sv + (ry + ri) * TWP + cx;
+#pragma unroll
+			for (int v = 0; v < NV; v++)
+				*reinterpret_cast<float4 *>(&w[4 * v]) = *reinterpret_cast<const float4 *>(wrow + 4 * v);
+			uint4 cc = *reinterpret_cast<const uint4 *>(scomb + (ry + ri) * CW_TX + cx);
+			uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
+			int L[4], Rr[4], LR[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				L[j] = c4[j] & 255;
+				Rr[j] = (c4[j] >> 8) & 255;
+				LR[j] = L[j] + Rr[j] - 1;              // taps of this row's run (:364-369)
+			}
+#pragma unroll
+			for (int oy = 0; oy < 2; oy++) {
+				const int delta = ri - oy - R;         // row offset from this output's centre row
+				if (delta < -R || delta > R) continue;
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					// row inside this output's vertical arm (:361): centre row iff the output is valid
+					const int va = delta < 0 ? U[oy][j] : Dn[oy][j];
+					const int vthr = delta < 0 ? -delta : delta;  // delta == 0: Dn > 0
+					row_taps<R>(acc[oy][j], cnt[oy][j], &w[j], L[j], Rr[j], LR[j], va, vthr);
+				}
+			}
+		}
+#pragma unroll
+		for (int oy = 0; oy < 2; oy++) {
+			const int y = y0 + ry + oy;
+			if (y >= H) continue;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int x = x0 + cx + j;
+				if (x >= W) continue;
+				const int xs = x + d * direction;
+				float res = (xs < 0 || xs >= W) ? sv[(ry + oy + R) * TWP + cx + j + R]      // :353-354
+								: acc[oy][j] / (float)cnt[oy][j];          // :373
+				out[(long)d * HW + (long)y * W + x] = res;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------ cbca, shared-memory tile with run loops
+// (arms of 6..14 pixels, e.g. the Middlebury presets)
 constexpr int CB_TX = 64, CB_TY = 16, CB_DCH = 16, CB_NT = 256;
 
 template <int R>  // halo = longest arm - 1
 __global__ void __launch_bounds__(CB_NT)
-cbca_tile_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
+cbca_loop_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
 		 const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction)
 {
 	constexpr int TH = CB_TY + 2 * R;          // tile rows incl. halo
@@ -181,10 +381,26 @@ __global__ void cbca_generic_kernel(const float *__restrict__ x0c, const float *
 }
 
 template <int R>
+int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int direction, cudaStream_t s)
+{
+	using Cfg = CWCfg<R>;
+	static bool attr_done[64] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!attr_done[dev & 63]) {
+		ADC_CUDA(cudaFuncSetAttribute(cbca_win_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+		attr_done[dev & 63] = true;
+	}
+	dim3 grid(adc_div_up(W, CW_TX), adc_div_up(H, CW_TY), adc_div_up(D, CW_DCH));
+	cbca_win_kernel<R><<<grid, CW_NT, Cfg::SMEM, s>>>(a0, a1, vol, out, D, H, W, direction);
+	return 0;
+}
+
+template <int R>
 void launch_tile(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int direction, cudaStream_t s)
 {
 	dim3 grid(adc_div_up(W, CB_TX), adc_div_up(H, CB_TY), adc_div_up(D, CB_DCH));
-	cbca_tile_kernel<R><<<grid, CB_NT, 0, s>>>(a0, a1, vol, out, D, H, W, direction);
+	cbca_loop_kernel<R><<<grid, CB_NT, 0, s>>>(a0, a1, vol, out, D, H, W, direction);
 }
 
 }  // namespace
@@ -202,8 +418,8 @@ int adc_cbca_packed(const uint32_t *a0, const uint32_t *a1, const float *x0c, co
 		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s)
 {
 	int halo = maxlen - 1;
-	if (halo <= 1) launch_tile<1>(a0, a1, vol, out, D, H, W, direction, s);
-	else if (halo <= 4) launch_tile<4>(a0, a1, vol, out, D, H, W, direction, s);
+	if (halo <= 1) { int rc = launch_win<1>(a0, a1, vol, out, D, H, W, direction, s); if (rc) return rc; }
+	else if (halo <= 4) { int rc = launch_win<4>(a0, a1, vol, out, D, H, W, direction, s); if (rc) return rc; }
 	else if (halo <= 8) launch_tile<8>(a0, a1, vol, out, D, H, W, direction, s);
 	else if (halo <= 13) launch_tile<13>(a0, a1, vol, out, D, H, W, direction, s);
 	else {

@@ -17,7 +17,8 @@
 int adc_pack_arms(const float *xc, uint32_t *packed, int H, int W, int *maxlen_dev, cudaStream_t s);
 int adc_cbca_packed(const uint32_t *a0, const uint32_t *a1, const float *x0c, const float *x1c,
 		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s);
-int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, int H, int W, int D,
+size_t adc_sgm_table_bytes(int H, int W, int D);
+int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, uint8_t *tab, int H, int W, int D,
 	     float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
 	     bool zero_out, cudaStream_t s);
 
@@ -36,6 +37,7 @@ struct mccnn_pipeline {
 	int *maxlen;
 	float *maps;      // 8HW: disparity maps and stage outputs
 	float *gauss;     // ks*ks
+	uint8_t *sgmtab;  // SGM penalty-class tables
 	int ks;
 	// staging for the host-buffer entry point
 	float *h_feat, *h_img, *h_disp;  // device copies: 2F, 2HW, HW
@@ -84,6 +86,7 @@ extern "C" int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, 
 	if (!rc) rc = dev_alloc((void **)&p->packed, 2 * p->HW * sizeof(uint32_t), &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->maxlen, sizeof(int), &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->maps, 8 * p->HW * f, &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->sgmtab, adc_sgm_table_bytes(H, W, D), &p->bytes);
 	p->ks = mccnn_gaussian(params->blur_sigma, nullptr);
 	if (!rc) rc = dev_alloc((void **)&p->gauss, (size_t)p->ks * p->ks * f, &p->bytes);
 	if (!rc) {
@@ -105,7 +108,7 @@ extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
 	if (!p) return;
 	DeviceGuard g(p->device);
 	cudaFree(p->vols); cudaFree(p->bufA); cudaFree(p->bufC); cudaFree(p->x0c); cudaFree(p->x1c);
-	cudaFree(p->packed); cudaFree(p->maxlen); cudaFree(p->maps); cudaFree(p->gauss);
+	cudaFree(p->packed); cudaFree(p->maxlen); cudaFree(p->maps); cudaFree(p->gauss); cudaFree(p->sgmtab);
 	cudaFree(p->h_feat); cudaFree(p->h_img); cudaFree(p->h_disp);
 	if (p->own_stream) cudaStreamDestroy(p->own_stream);
 	delete p;
@@ -158,10 +161,10 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 		}
 		for (int it = 0; it < o.sgm_i; it++) {                                                   // :1008-1020
 			STEP(mccnn_transpose_dhw_to_hwd(cur, spare, D, H, W, s));                            // :1008
-			STEP(adc_sgm2(imgL, imgR, spare, p->bufC, H, W, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
+			STEP(adc_sgm2(imgL, imgR, spare, p->bufC, p->sgmtab, H, W, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
 				      o.sgm_q1, o.sgm_q2, direction, /*zero_out=*/true, s));                     // :1014-1016
 			STEP(mccnn_transpose_hwd_to_dhw_div4(p->bufC, cur, D, H, W, s));                     // :1017-1020
-			nl += 6;
+			nl += 7;
 		}
 		for (int i = 0; i < o.cbca_i2; i++) {                                                    // :1035-1038
 			STEP(adc_cbca_packed(p->packed, p->packed + HW, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, s));

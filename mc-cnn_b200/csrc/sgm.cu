@@ -3,24 +3,33 @@
 // Replaces adcensus.cu:535-697: the reference launches one kernel per scan step
 // (2*(W+H) = 3192 launches at 370x1226), each block re-reading the previous
 // step's line state from global `tmp` and tree-reducing the min over D in shared
-// memory.  Here one launch does a whole direction: ONE WARP PER SCANLINE keeps
-// the line state L_r(p-r, .) in registers for the entire scan (lane l owns the K
-// consecutive disparities l*K..l*K+K-1), the min over D is a register reduction
-// + warp shuffle, the d-1 / d+1 neighbours are registers (one shuffle each at
-// the lane boundary), and the next pixels' cost/accumulator vectors are
-// prefetched PF steps ahead so the serial recurrence overlaps HBM latency.
+// memory.  Here one launch does a whole direction:
+//   * ONE WARP PER SCANLINE keeps the line state L_r(p-r, .) in registers for the
+//     entire scan; lane l owns the K consecutive disparities l*K .. l*K+K-1;
+//   * the min over D is a K-element register tree + one `redux.sync.min.f32`
+//     (CREDUX, sm_100a) instead of a shared-memory tree with 9 barriers;
+//   * the d-1 / d+1 neighbours are registers (one shuffle each at lane borders);
+//   * the cost vectors of the next PF pixels stream into a per-warp shared-memory
+//     ring with cp.async (16-byte granules, each lane fetching exactly the
+//     elements it will consume, so no barrier is needed), which keeps ~PF*2 KB per
+//     warp in flight and hides HBM latency behind the serial recurrence;
+//   * the P1/P2 selection (adcensus.cu:586-605) is table driven: a pre-pass
+//     classifies |I(p) - I(p-r)| against tau_so once per image / scan axis into
+//     byte tables (padded by D columns of the out-of-image class, D2 = 10), so a
+//     step needs one byte per disparity instead of two image loads and two
+//     bounds checks.
 //
-// Arithmetic is the reference's, expression for expression (adds, fminf,
-// IEEE divisions; no contractible multiply-add), and `out` is accumulated in the
-// reference's direction order (right, left, down, up) => bit-identical results
-// for volumes whose valid disparities form a prefix per pixel (what StereoJoin /
-// ad / census produce).  Padding slots d >= D are carried as NaN, which fminf
-// ignores exactly like the reference's `d + 1 < size3` guard.
+// Arithmetic is the reference's, expression for expression (adds, fminf, IEEE
+// divisions; nothing contractible), and `out` is accumulated in the reference's
+// direction order (right, left, down, up) => bit-identical results for volumes
+// whose valid disparities form a prefix per pixel (what StereoJoin / ad / census
+// produce).  Padding slots d >= D are carried as NaN, which fminf ignores exactly
+// like the reference's `d + 1 < size3` guard.
 //
 // Layout: input/output (H,W,D) like the reference (INDEX, adcensus.cu:531-533).
-// Algorithmic traffic per call: the 4 passes each read `input` and read-modify-
-// write `output`: 4 * 3V bytes (V = 4*D*H*W); the first pass skips the read of a
-// caller-zeroed output when told so (pipeline) -> 11V.
+// Algorithmic traffic per call: 4 passes x (read input + read-modify-write
+// output) = 12V bytes (V = 4*D*H*W); 11V when the caller guarantees a zeroed
+// output (pipeline), because the first pass then skips the read.
 #include "common.cuh"
 
 namespace {
@@ -30,29 +39,88 @@ struct SgmParams {
 	int direction;
 };
 
-__device__ __forceinline__ float warp_min_nanskip(float v)
+// ---------------------------------------------------------------- penalty class tables
+// class of a colour difference against tau_so: 0 (< tau), 2 (> tau), 1 otherwise (== tau or NaN):
+// exactly the three branches of adcensus.cu:596-605.
+__device__ __forceinline__ uint8_t sgm_class(float diff, float tau)
 {
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-	return v;
+	return diff < tau ? 0 : (diff > tau ? 2 : 1);
+}
+
+// tab layout: 4 planes [h0, v0, h1, v1], each H rows of pitch Wp = W + 2*pad bytes, image column
+// j at byte pad + j.  h: |I[y][j] - I[y][j-1]|, v: |I[y][j] - I[y-1][j]|; entries whose
+// neighbour is outside the image, and the padding, hold the class of D2 = 10 (adcensus.cu:591).
+// Plane 0/1 from x0 (D1, always in range where used), plane 2/3 from x1 (D2).
+__global__ void sgm_class_kernel(const float *__restrict__ x0, const float *__restrict__ x1, uint8_t *__restrict__ tab,
+				 int H, int W, int pad, float tau)
+{
+	const int Wp = W + 2 * pad;
+	const long plane = (long)H * Wp;
+	long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= plane) return;
+	int y = (int)(id / Wp), j = (int)(id % Wp) - pad;
+	const uint8_t oob = sgm_class(10.0f, tau);
+	uint8_t h0 = oob, v0 = oob, h1 = oob, v1 = oob;
+	if (j >= 0 && j < W) {
+		long p = (long)y * W + j;
+		if (j >= 1) {
+			h0 = sgm_class(fabsf(x0[p] - x0[p - 1]), tau);
+			h1 = sgm_class(fabsf(x1[p] - x1[p - 1]), tau);
+		}
+		if (y >= 1) {
+			v0 = sgm_class(fabsf(x0[p] - x0[p - W]), tau);
+			v1 = sgm_class(fabsf(x1[p] - x1[p - W]), tau);
+		}
+	}
+	tab[id] = h0;
+	tab[plane + id] = v0;
+	tab[2 * plane + id] = h1;
+	tab[3 * plane + id] = v1;
+}
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ float warp_min_f32(float v)
+{
+	float r;
+	asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));  // NaN inputs are skipped
+	return r;
+}
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
 
 template <int K, bool VEC>
-__device__ __forceinline__ void load_vec(float (&r)[K], const float *p, int dbase, int D)
+__device__ __forceinline__ void issue_vec(float *slot, const float *g, int dbase, int D)
 {
 	if constexpr (VEC) {
 #pragma unroll
+		for (int k = 0; k < K; k += 4)
+			if (dbase + k < D) cp_async16(slot + k, g + k);
+	} else {
+#pragma unroll
+		for (int k = 0; k < K; k++)
+			if (dbase + k < D) cp_async4(slot + k, g + k);
+	}
+}
+
+template <int K>
+__device__ __forceinline__ void read_slot(float (&r)[K], const float *slot)
+{
+	if constexpr (K % 4 == 0) {
+#pragma unroll
 		for (int k = 0; k < K; k += 4) {
-			if (dbase + k < D) {
-				float4 v = *reinterpret_cast<const float4 *>(p + k);
-				r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
-			} else {
-				r[k] = r[k + 1] = r[k + 2] = r[k + 3] = adc_nan();
-			}
+			float4 v = *reinterpret_cast<const float4 *>(slot + k);
+			r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
 		}
 	} else {
 #pragma unroll
-		for (int k = 0; k < K; k++) r[k] = (dbase + k < D) ? p[k] : adc_nan();
+		for (int k = 0; k < K; k++) r[k] = slot[k];
 	}
 }
 
@@ -70,43 +138,62 @@ __device__ __forceinline__ void store_vec(const float (&r)[K], float *p, int dba
 	}
 }
 
+// ---------------------------------------------------------------- one scan direction
 // SD: 0 right, 1 left, 2 down, 3 up (adcensus.cu:541-565).  ZERO: output known to be 0 on entry.
-template <int K, bool VEC, int SD, bool ZERO, int PF>
-__global__ void __launch_bounds__(128)
-sgm_pass_kernel(const float *__restrict__ x0, const float *__restrict__ x1,
-		const float *__restrict__ in, float *__restrict__ out,
-		int H, int W, int D, SgmParams prm)
+template <int K, bool VEC, int SD, bool ZERO, int PF, int WPB>
+__global__ void __launch_bounds__(32 * WPB)
+sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, float *__restrict__ out,
+		int H, int W, int D, int pad, SgmParams prm)
 {
-	const int lane = threadIdx.x & 31;
-	const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	extern __shared__ __align__(16) float sgm_smem[];
+	constexpr int VSZ = 32 * K;                    // floats per cost vector slot (padded to 32*K)
+	constexpr int NV = ZERO ? 1 : 2;               // ring holds `in` (and `out` unless ZERO)
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int line = blockIdx.x * WPB + wib;
 	const int nlines = SD < 2 ? H : W;
 	const int nsteps = SD < 2 ? W : H;
-	if (line >= nlines) return;
+	if (line >= nlines) return;                    // whole warp
 
 	constexpr int dx = SD == 0 ? 1 : (SD == 1 ? -1 : 0);
 	constexpr int dy = SD == 2 ? 1 : (SD == 3 ? -1 : 0);
 	const int dbase = lane * K;
-	const int direction = prm.direction;
-	const float tau = prm.tau_so;
+	float *ring = sgm_smem + (size_t)wib * PF * NV * VSZ + dbase;   // this lane's K floats of slot 0
+
 	// adcensus.cu:595-605 and :609/:612, same expressions
 	const float P1f = prm.pi1, P2f = prm.pi2;
 	const float P1s = prm.pi1 / (prm.q1 * prm.q2), P2s = prm.pi2 / (prm.q1 * prm.q2);
 	const float P1m = prm.pi1 / prm.q1, P2m = prm.pi2 / prm.q1;
 	const float P1f_a = P1f / prm.alpha1, P1s_a = P1s / prm.alpha1, P1m_a = P1m / prm.alpha1;
 
-	// pixel of scan step s on this line, and the element stride between steps
+	// class tables: D1 from plane (SD<2 ? 0 : 1), D2 from plane (SD<2 ? 2 : 3).  The stored
+	// difference at (y, j) pairs pixel j with its left / upper neighbour, so scans that look
+	// right / down (dx = -1, dy = -1) read the entry one further.
+	const int Wp = W + 2 * pad;
+	const long plane = (long)H * Wp;
+	const uint8_t *t1 = tab + (SD < 2 ? 0 : 1) * plane + pad;
+	const uint8_t *t2 = tab + (SD < 2 ? 2 : 3) * plane + pad;
+	constexpr int tshift_x = dx < 0 ? 1 : 0;
+	constexpr int tshift_y = dy < 0 ? 1 : 0;
+
 	int x = SD == 0 ? 0 : (SD == 1 ? W - 1 : line);
 	int y = SD == 2 ? 0 : (SD == 3 ? H - 1 : line);
 	const long pix_step = (long)(dy * W + dx) * D;
 	long base = ((long)y * W + x) * D + dbase;
+	const int ddir = prm.direction;
 
-	float rin[PF][K], rout[PF][K];
+	// NaN in the padding slots (never overwritten), then fill the ring
 #pragma unroll
-	for (int u = 0; u < PF; u++)
+	for (int s = 0; s < PF * NV; s++)
+#pragma unroll
+		for (int k = 0; k < K; k++) ring[s * VSZ + k] = adc_nan();
+#pragma unroll
+	for (int u = 0; u < PF; u++) {
 		if (u < nsteps) {
-			load_vec<K, VEC>(rin[u], in + base + u * pix_step, dbase, D);
-			if (!ZERO) load_vec<K, VEC>(rout[u], out + base + u * pix_step, dbase, D);
+			issue_vec<K, VEC>(ring + (u * NV) * VSZ, in + base + u * pix_step, dbase, D);
+			if (!ZERO) issue_vec<K, VEC>(ring + (u * NV + 1) * VSZ, out + base + u * pix_step, dbase, D);
 		}
+		asm volatile("cp.async.commit_group;");
+	}
 
 	float prev[K];
 	for (int s0 = 0; s0 < nsteps; s0 += PF) {
@@ -114,103 +201,136 @@ sgm_pass_kernel(const float *__restrict__ x0, const float *__restrict__ x1,
 		for (int u = 0; u < PF; u++) {
 			const int s = s0 + u;
 			if (s >= nsteps) break;
+			asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1));
+			float cin[K], cout[K];
+			read_slot<K>(cin, ring + (u * NV) * VSZ);
+			if (!ZERO) read_slot<K>(cout, ring + (u * NV + 1) * VSZ);
+
 			float val[K];
 			if (s == 0) {                                   // adcensus.cu:567-572
 #pragma unroll
-				for (int k = 0; k < K; k++) val[k] = rin[u][k];
+				for (int k = 0; k < K; k++) val[k] = cin[k];
 			} else {
-				float mloc = prev[0];
+				float mt[K];
 #pragma unroll
-				for (int k = 1; k < K; k++) mloc = fminf(mloc, prev[k]);
-				const float m = warp_min_nanskip(mloc);         // :579-584
+				for (int k = 0; k < K; k++) mt[k] = prev[k];
+#pragma unroll
+				for (int w = K / 2; w > 0; w >>= 1)
+#pragma unroll
+					for (int k = 0; k < w; k++) mt[k] = fminf(mt[k], mt[k + w]);
+				const float m = warp_min_f32(mt[0]);            // :579-584
 				float left = __shfl_up_sync(0xffffffffu, prev[K - 1], 1);
 				float right = __shfl_down_sync(0xffffffffu, prev[0], 1);
 				if (lane == 0) left = adc_nan();                // d - 1 < 0 (:608)
 				if (lane == 31) right = adc_nan();
 
-				const int ind2 = y * W + x;
-				const float D1 = fabsf(__ldg(x0 + ind2) - __ldg(x0 + ind2 - dy * W - dx)); // :587
-				const bool c1lt = D1 < tau, c1gt = D1 > tau;
+				const int ty = y + tshift_y;                    // row / column of the stored difference
+				const uint8_t c1 = __ldg(t1 + (long)ty * Wp + x + tshift_x);          // D1 class (:587)
+				const uint8_t *c2p = t2 + (long)ty * Wp + x + tshift_x + dbase * ddir;  // D2 classes (:588-594)
+				// penalties when the D2 class equals the D1 class (both < tau or both > tau), else middle
+				const bool c1lt = c1 == 0;
+				const float P1e = c1 == 1 ? P1m : (c1lt ? P1f : P1s);
+				const float P2e = c1 == 1 ? P2m : (c1lt ? P2f : P2s);
+				const float P1ae = c1 == 1 ? P1m_a : (c1lt ? P1f_a : P1s_a);
 #pragma unroll
 				for (int k = 0; k < K; k++) {
-					const int xx = x + (dbase + k) * direction;
-					float D2;
-					if (xx < 0 || xx >= W || xx - dx < 0 || xx - dx >= W) D2 = 10.0f;      // :590-591
-					else D2 = fabsf(__ldg(x1 + y * W + xx) - __ldg(x1 + (y - dy) * W + xx - dx)); // :593
-					float P1, P2, P1a;
-					if (c1lt && D2 < tau) { P1 = P1f; P2 = P2f; P1a = P1f_a; }
-					else if (c1gt && D2 > tau) { P1 = P1s; P2 = P2s; P1a = P1s_a; }
-					else { P1 = P1m; P2 = P2m; P1a = P1m_a; }
+					const bool eq = __ldg(c2p + k * ddir) == c1;
+					const float P1 = eq ? P1e : P1m, P2 = eq ? P2e : P2m, P1a = eq ? P1ae : P1m_a;
 					const float pm = k > 0 ? prev[k - 1] : left;
 					const float pp = k < K - 1 ? prev[k + 1] : right;
 					float cost = fminf(prev[k], m + P2);                               // :607
 					cost = fminf(cost, pm + (SD == 2 ? P1a : P1));                     // :609
 					cost = fminf(cost, pp + (SD == 3 ? P1a : P1));                     // :612
-					val[k] = rin[u][k] + cost - m;                                     // :615
+					val[k] = cin[k] + cost - m;                                        // :615
 				}
 			}
 			float o[K];
 #pragma unroll
 			for (int k = 0; k < K; k++) {
-				o[k] = (ZERO ? 0.0f : rout[u][k]) + val[k];                            // :569 / :616
+				o[k] = (ZERO ? 0.0f : cout[k]) + val[k];                               // :569 / :616
 				prev[k] = val[k];                                                      // :570 / :617
 			}
 			store_vec<K, VEC>(o, out + base, dbase, D);
-			// refill this ring slot with step s + PF
+			// refill this ring slot with step s + PF (its values are in registers by now)
 			if (s + PF < nsteps) {
-				load_vec<K, VEC>(rin[u], in + base + PF * pix_step, dbase, D);
-				if (!ZERO) load_vec<K, VEC>(rout[u], out + base + PF * pix_step, dbase, D);
+				issue_vec<K, VEC>(ring + (u * NV) * VSZ, in + base + PF * pix_step, dbase, D);
+				if (!ZERO) issue_vec<K, VEC>(ring + (u * NV + 1) * VSZ, out + base + PF * pix_step, dbase, D);
 			}
+			asm volatile("cp.async.commit_group;");
 			base += pix_step;
 			x += dx;
 			y += dy;
 		}
 	}
+	asm volatile("cp.async.wait_group 0;");
 }
 
-template <int K, bool VEC, int SD>
-int launch_pass(const float *x0, const float *x1, const float *in, float *out, int H, int W, int D,
-		const SgmParams &prm, bool zero, cudaStream_t s)
+template <int K, bool VEC, int SD, bool ZERO>
+int launch_pass(const uint8_t *tab, const float *in, float *out, int H, int W, int D, int pad,
+		const SgmParams &prm, cudaStream_t s)
 {
-	constexpr int PF = K >= 16 ? 2 : 4;
-	const int nlines = SD < 2 ? H : W;
+	constexpr int PF = K >= 16 ? 6 : 8;
 	// horizontal scans have few, long lines: one warp per CTA spreads them over all SMs
-	const int wpb = SD < 2 ? 1 : 4;
-	dim3 grid(adc_div_up(nlines, wpb)), block(32 * wpb);
-	if (zero) sgm_pass_kernel<K, VEC, SD, true, PF><<<grid, block, 0, s>>>(x0, x1, in, out, H, W, D, prm);
-	else sgm_pass_kernel<K, VEC, SD, false, PF><<<grid, block, 0, s>>>(x0, x1, in, out, H, W, D, prm);
+	constexpr int WPB = SD < 2 ? 1 : 4;
+	constexpr int NV = ZERO ? 1 : 2;
+	constexpr int SMEM = WPB * PF * NV * 32 * K * 4;
+	auto kern = sgm_pass_kernel<K, VEC, SD, ZERO, PF, WPB>;
+	if (SMEM > 48 * 1024) {
+		static bool done[64] = {false};
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (!done[dev & 63]) {
+			ADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+			done[dev & 63] = true;
+		}
+	}
+	const int nlines = SD < 2 ? H : W;
+	kern<<<adc_div_up(nlines, WPB), 32 * WPB, SMEM, s>>>(tab, in, out, H, W, D, pad, prm);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
 
 template <int K, bool VEC>
-int launch_all(const float *x0, const float *x1, const float *in, float *out, int H, int W, int D,
+int launch_all(const uint8_t *tab, const float *in, float *out, int H, int W, int D, int pad,
 	       const SgmParams &prm, bool zero_out, cudaStream_t s)
 {
 	int rc;
-	if ((rc = launch_pass<K, VEC, 0>(x0, x1, in, out, H, W, D, prm, zero_out, s))) return rc;
-	if ((rc = launch_pass<K, VEC, 1>(x0, x1, in, out, H, W, D, prm, false, s))) return rc;
-	if ((rc = launch_pass<K, VEC, 2>(x0, x1, in, out, H, W, D, prm, false, s))) return rc;
-	return launch_pass<K, VEC, 3>(x0, x1, in, out, H, W, D, prm, false, s);
+	rc = zero_out ? launch_pass<K, VEC, 0, true>(tab, in, out, H, W, D, pad, prm, s)
+		      : launch_pass<K, VEC, 0, false>(tab, in, out, H, W, D, pad, prm, s);
+	if (rc) return rc;
+	if ((rc = launch_pass<K, VEC, 1, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
+	if ((rc = launch_pass<K, VEC, 2, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
+	return launch_pass<K, VEC, 3, false>(tab, in, out, H, W, D, pad, prm, s);
 }
 
 }  // namespace
 
-// zero_out: `output` is known to be all zeros (main.lua:1014) -> first pass skips reading it
-int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, int H, int W, int D,
+// lanes carry 32*K disparity slots (K from D); the class tables are padded by that many columns so
+// that the padding slots d >= D also index inside the row
+static int sgm_slots(int D) { return D <= 32 ? 32 : (D <= 64 ? 64 : (D <= 128 ? 128 : (D <= 256 ? 256 : 512))); }
+
+size_t adc_sgm_table_bytes(int H, int W, int D) { return 4 * (size_t)H * (W + 2 * (size_t)sgm_slots(D)) + 16; }
+
+// zero_out: `output` is known to be all zeros (main.lua:1014) -> first pass skips reading it.
+// tab: scratch of adc_sgm_table_bytes(H, W, D) bytes.
+int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, uint8_t *tab, int H, int W, int D,
 	     float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
 	     bool zero_out, cudaStream_t s)
 {
 	SgmParams prm{pi1, pi2, tau_so, alpha1, q1, q2, direction};
+	const int pad = sgm_slots(D);
+	const long plane = (long)H * (W + 2 * pad);
+	sgm_class_kernel<<<adc_div_up(plane, 256), 256, 0, s>>>(x0, x1, tab, H, W, pad, tau_so);
+	ADC_CHECK_LAUNCH();
 	const bool vec = (D % 4 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0);
-	if (D <= 32) return launch_all<1, false>(x0, x1, in, out, H, W, D, prm, zero_out, s);
-	if (D <= 64) return launch_all<2, false>(x0, x1, in, out, H, W, D, prm, zero_out, s);
-	if (D <= 128) return vec ? launch_all<4, true>(x0, x1, in, out, H, W, D, prm, zero_out, s)
-				 : launch_all<4, false>(x0, x1, in, out, H, W, D, prm, zero_out, s);
-	if (D <= 256) return vec ? launch_all<8, true>(x0, x1, in, out, H, W, D, prm, zero_out, s)
-				 : launch_all<8, false>(x0, x1, in, out, H, W, D, prm, zero_out, s);
-	return vec ? launch_all<16, true>(x0, x1, in, out, H, W, D, prm, zero_out, s)
-		   : launch_all<16, false>(x0, x1, in, out, H, W, D, prm, zero_out, s);
+	if (D <= 32) return launch_all<1, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
+	if (D <= 64) return launch_all<2, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
+	if (D <= 128) return vec ? launch_all<4, true>(tab, in, out, H, W, D, pad, prm, zero_out, s)
+				 : launch_all<4, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
+	if (D <= 256) return vec ? launch_all<8, true>(tab, in, out, H, W, D, pad, prm, zero_out, s)
+				 : launch_all<8, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
+	return vec ? launch_all<16, true>(tab, in, out, H, W, D, pad, prm, zero_out, s)
+		   : launch_all<16, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
 }
 
 extern "C" int adcensus_sgm2(const float *x0, const float *x1, const float *input, float *output, float *tmp,
@@ -221,6 +341,11 @@ extern "C" int adcensus_sgm2(const float *x0, const float *x1, const float *inpu
 	if (!x0 || !x1 || !input || !output || input == output) return ADCENSUS_EINVAL;
 	if (H < 1 || W < 1 || D < 1 || (direction != 1 && direction != -1)) return ADCENSUS_EINVAL;
 	if (D > ADCENSUS_MAX_DISP) return ADCENSUS_ELIMIT;
-	return adc_sgm2(x0, x1, input, output, H, W, D, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction,
-			false, adc_stream(stream));
+	cudaStream_t s = adc_stream(stream);
+	uint8_t *tab = nullptr;
+	int rc = adc_scratch_alloc((void **)&tab, adc_sgm_table_bytes(H, W, D), s);
+	if (rc) return rc;
+	rc = adc_sgm2(x0, x1, input, output, tab, H, W, D, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction, false, s);
+	int rc2 = adc_scratch_free(tab, s);
+	return rc ? rc : rc2;
 }
