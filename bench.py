@@ -202,7 +202,7 @@ def stage_table(cfg, opt, dev_in, iters=5):
     t["cross"] = time_op(lambda: adcensus.cross(iL, x0c, opt.L1, opt.tau1), iters, flush)
     adcensus.cross(iR, x1c, opt.L1, opt.tau1)
     tmp = torch.empty((1, D, H, W), device=dev)
-    t["cbca"] = time_op(lambda: adcensus.cbca(x0c, x1c, vols[0:1], tmp, -1), iters, flush)
+    t["cbca"] = time_op(lambda: adcensus.cbca(x0c, x1c, vols[0:1], tmp, -1, max_arm=max(opt.L1, 2)), iters, flush)
     volt = adcensus.transpose_dhw_to_hwd(vols[0:1])
     t["transpose"] = time_op(lambda: adcensus.lib().mccnn_transpose_dhw_to_hwd(
         adcensus._t(vols[0:1], 1, "t"), adcensus._t(volt, 2, "t"), D, H, W, adcensus._stream(volt)), iters, flush)
@@ -250,6 +250,9 @@ def run_b200(args):
     import mccnn_b200  # noqa: F401
     from mccnn_b200 import adcensus, pipeline
 
+    # keep stdout clean for the one JSON line (NCCL / torch may print banners there)
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = dist_setup(args)
     cfg = dict(WORKLOAD)
     if args.small:
@@ -347,7 +350,7 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out), flush=True)
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 def run_reference(args):

@@ -63,6 +63,11 @@ int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1
 int adcensus_cbca(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 		  int D, int H, int W, int direction, adcensus_stream_t stream);
 
+/* Same, without the host synchronisation: the caller states the longest arm cross() can have
+ * produced for these arms, max(L1, 2) (main.lua knows opt.L1).  Asynchronous on `stream`. */
+int adcensus_cbca_ex(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+		     int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream);
+
 /* adcensus.sgm2(x0, x1, input, output, tmp, pi1, pi2, tau_so, alpha1, sgm_q1,
  *               sgm_q2, direction)  adcensus.cu:535-697
  * input/output are (H,W,D); output is accumulated into (+=) in the order right,

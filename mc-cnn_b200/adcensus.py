@@ -92,13 +92,19 @@ def cross(x0, out, L1, tau1):
         _check(lib().adcensus_cross(p0, po, H, W, int(L1), _f(tau1), _stream(out)), n)
 
 
-def cbca(x0c, x1c, vol_in, vol_out, direction):
-    """adcensus.cbca(x0c, x1c, vol_in, vol_out, direction)  adcensus.cu:379-400"""
+def cbca(x0c, x1c, vol_in, vol_out, direction, max_arm=None):
+    """adcensus.cbca(x0c, x1c, vol_in, vol_out, direction)  adcensus.cu:379-400
+
+    ``max_arm`` (extension): the longest arm cross() can have produced, max(L1, 2); when given the
+    call is fully asynchronous (adcensus_cbca_ex), otherwise the library reads it back once."""
     n = "cbca"
     a, b, vi, vo = _t(x0c, 1, n), _t(x1c, 2, n), _t(vol_in, 3, n), _t(vol_out, 4, n)
     D, H, W = vol_out.size(1), vol_out.size(2), vol_out.size(3)
     with torch.cuda.device(vol_out.device):
-        _check(lib().adcensus_cbca(a, b, vi, vo, D, H, W, int(direction), _stream(vol_out)), n)
+        if max_arm is None:
+            _check(lib().adcensus_cbca(a, b, vi, vo, D, H, W, int(direction), _stream(vol_out)), n)
+        else:
+            _check(lib().adcensus_cbca_ex(a, b, vi, vo, D, H, W, int(direction), int(max_arm), _stream(vol_out)), n)
 
 
 def sgm2(x0, x1, input, output, tmp, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction):

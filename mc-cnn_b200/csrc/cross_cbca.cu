@@ -439,6 +439,25 @@ extern "C" int adcensus_cross(const float *x0, float *out, int H, int W, int L1,
 	return 0;
 }
 
+extern "C" int adcensus_cbca_ex(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+				int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream)
+{
+	if (!x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
+	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1) || max_arm < 1) return ADCENSUS_EINVAL;
+	cudaStream_t s = adc_stream(stream);
+	long HW = (long)H * W;
+	uint32_t *packed = nullptr;
+	int rc = adc_scratch_alloc((void **)&packed, (2 * HW + 1) * sizeof(uint32_t), s);
+	if (rc) return rc;
+	int *maxlen_dev = (int *)(packed + 2 * HW);
+	rc = (int)cudaMemsetAsync(maxlen_dev, 0, sizeof(int), s);
+	if (!rc) rc = adc_pack_arms(x0c, packed, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_pack_arms(x1c, packed + HW, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_cbca_packed(packed, packed + HW, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, s);
+	int rc2 = adc_scratch_free(packed, s);
+	return rc ? rc : rc2;
+}
+
 extern "C" int adcensus_cbca(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 			     int D, int H, int W, int direction, adcensus_stream_t stream)
 {

@@ -304,6 +304,38 @@ def test_against_live_reference():
         sp.close()
 
 
+def test_lua_face_through_the_reference_driver(oracle):
+    """luaopen_libadcensus of OUR library (shim build), called by the very driver that calls the
+    reference's: same 31 names, same positional signatures, same results."""
+    from oracle import refdriver
+
+    if not os.path.exists(refdriver.LUAFACE_LIB):
+        pytest.skip("oracle/_ref/libadcensus_luaface.so not built")
+    ours = refdriver.ShimLibrary(refdriver.LUAFACE_LIB)
+    names = ours.functions("adcensus")
+    assert len(names) == 31 and ours.functions("nn") == ["SpatialLogSoftMax_updateOutput", "SpatialLogSoftMax_updateGradInput"]
+    if os.path.exists(refdriver.REF_LIB):
+        assert names == refdriver.ShimLibrary(refdriver.REF_LIB).functions("adcensus")  # adcensus.cu:2061-2096
+    H, W, C, D = 36, 80, 16, 18
+    opt = pipeline.make_params("kitti2015", "slow", cbca_i2=2)
+    p = synth.make_pair(H, W, C, D, seed=5)
+    want, wL, wR = oracle.stereo_predict(p["featL"], p["featR"], p["imgL"], p["imgR"], D,
+                                         oracle.Params(**opt.as_dict()), want_vols=True)
+    x_batch = cu(np.stack([p["imgL"], p["imgR"]])[:, None])
+    feats = cu(np.stack([p["featL"], p["featR"]]))
+    d, vL, vR = refdriver.stereo_predict(ours, x_batch, feats, opt, D, want_vols=True)
+    same(vL, wL, "left.bin (Lua face)")
+    same(vR, wR, "right.bin (Lua face)")
+    same(d, want, "disp.bin (Lua face)")
+    # type errors and out-of-scope names raise Lua errors
+    with pytest.raises(refdriver.ShimError, match="torch.CudaTensor expected"):
+        ours.call("cross", 1.0, x_batch[0], 5, 0.1)
+    with pytest.raises(refdriver.ShimError, match="not implemented"):
+        ours.call("Margin2", x_batch[0], x_batch[0], x_batch[0], 0.2, 1)
+    with pytest.raises(refdriver.ShimError, match="nil value"):
+        ours.call("no_such_function")
+
+
 def test_error_behaviour():
     """wrong tensor types raise like luaT_checkudata; limits are rejected, not overflowed"""
     with pytest.raises(adcensus.AdcensusError):
