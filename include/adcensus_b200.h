@@ -122,6 +122,9 @@ int adcensus_census(const float *x0, const float *x1, float *out, int D, int nch
 
 /* vols:fill(0/0)  main.lua:946 */
 int mccnn_fill_nan(float *p, size_t n, adcensus_stream_t stream);
+/* the part of that fill StereoJoin does not overwrite: NaN where x < d (left volume) and x >= W - d
+ * (right volume); what the fused pipeline uses instead of filling 2V bytes */
+int mccnn_fill_invalid(float *volL, float *volR, int D, int H, int W, adcensus_stream_t stream);
 /* fix_border(net, vol, direction)  main.lua:922-927; n = (window-1)/2 */
 int mccnn_fix_border(float *vol, int D, int H, int W, int n, int direction, adcensus_stream_t stream);
 /* vol:transpose(2,3):transpose(3,4):clone()  main.lua:1008   (D,H,W) -> (H,W,D) */

@@ -16,6 +16,18 @@ int adc_num_sms()
 
 int adc_scratch_alloc(void **p, size_t bytes, cudaStream_t s)
 {
+	// keep freed scratch in the device's default pool instead of returning it to the OS at every
+	// synchronisation (the default release threshold is 0), so repeated op-level calls reuse it
+	static bool tuned[64] = {false};
+	int dev = 0;
+	if (cudaGetDevice(&dev) == cudaSuccess && !tuned[dev & 63]) {
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+			unsigned long long keep = ~0ULL;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+		tuned[dev & 63] = true;
+	}
 	return (int)cudaMallocAsync(p, bytes ? bytes : 4, s);
 }
 

@@ -136,7 +136,7 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 	int nl = 0;
 
 	float *volsL = p->vols, *volsR = p->vols + V;
-	STEP(mccnn_fill_nan(p->vols, (size_t)(2 * V), s)); nl += 1;                                  // main.lua:946
+	STEP(mccnn_fill_invalid(volsL, volsR, D, H, W, s)); nl += 1;                                 // main.lua:946 (only what :947 leaves)
 	STEP(adcensus_StereoJoin(featL, featR, volsL, volsR, C, D, H, W, s)); nl += 1;               // :947
 	STEP(mccnn_fix_border(volsL, D, H, W, o.border, -1, s));                                     // :948
 	STEP(mccnn_fix_border(volsR, D, H, W, o.border, 1, s)); nl += o.border ? 2 : 0;              // :949

@@ -282,6 +282,21 @@ __global__ void fill_nan_kernel(float4 *p4, size_t n4, float *tail, int ntail)
 	if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = q;
 }
 
+// NaN only where StereoJoin writes nothing (main.lua:946 fills everything; the op then overwrites the
+// rest): left volume x < d, right volume x >= W - d.  One thread per (d, y, t), t < d.
+__global__ void fill_invalid_kernel(float *volL, float *volR, int D, int H, int W)
+{
+	const int d = blockIdx.y + 1;                  // d = 0 has no invalid entries
+	const int n = min(d, W);
+	const long HW = (long)H * W;
+	const float q = adc_nan();
+	for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)H * n; i += (long)gridDim.x * blockDim.x) {
+		const int y = (int)(i / n), t = (int)(i % n);
+		volL[d * HW + (long)y * W + t] = q;
+		volR[d * HW + (long)y * W + (W - 1 - t)] = q;
+	}
+}
+
 __global__ void fix_border_kernel(float *vol, long rows, int W, int n, int direction)
 {
 	long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -321,17 +336,51 @@ __global__ void transpose_kernel(const float *__restrict__ in, float *__restrict
 		ADC_CHECK_LAUNCH();                                                   \
 	} while (0)
 
+// 64x64 tile, float4 on both sides (R and Cn multiples of 4, 16-byte aligned bases): each thread moves 4 float4 in
+// and 4 float4 out; gridDim.x rides the longer extent.
+template <bool LONGROWS>
+__global__ void __launch_bounds__(256)
+transpose64_kernel(const float *__restrict__ in, float *__restrict__ out, long R, long Cn, float div, bool do_div)
+{
+	__shared__ float t[64][65];
+	const long c0 = (long)(LONGROWS ? blockIdx.y : blockIdx.x) * 64;
+	const long r0 = (long)(LONGROWS ? blockIdx.x : blockIdx.y) * 64;
+	const int tid = threadIdx.x;
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const int idx = tid + 256 * i, row = idx >> 4, c4 = (idx & 15) * 4;
+		if (r0 + row < R && c0 + c4 < Cn) {
+			const float4 v = *reinterpret_cast<const float4 *>(in + (r0 + row) * Cn + c0 + c4);
+			t[row][c4] = v.x; t[row][c4 + 1] = v.y; t[row][c4 + 2] = v.z; t[row][c4 + 3] = v.w;
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const int idx = tid + 256 * i, c = idx >> 4, r4 = (idx & 15) * 4;
+		if (c0 + c < Cn && r0 + r4 < R) {
+			float4 v = make_float4(t[r4][c], t[r4 + 1][c], t[r4 + 2][c], t[r4 + 3][c]);
+			if (do_div) { v.x /= div; v.y /= div; v.z /= div; v.w /= div; }
+			*reinterpret_cast<float4 *>(out + (c0 + c) * R + r0 + r4) = v;
+		}
+	}
+}
+
 int adc_transpose(const float *in, float *out, long R, long Cn, float div, bool do_div, cudaStream_t s)
 {
-	dim3 block(32, 8);
+	const bool vec = (R % 4 == 0) && (Cn % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
+	const int tile = vec ? 64 : 32;
+	dim3 block = vec ? dim3(256) : dim3(32, 8);
 	if (R >= Cn) {
-		dim3 grid(adc_div_up(R, 32), adc_div_up(Cn, 32));
+		dim3 grid(adc_div_up(R, tile), adc_div_up(Cn, tile));
 		if (grid.y > 65535) return ADCENSUS_ELIMIT;
-		transpose_kernel<true><<<grid, block, 0, s>>>(in, out, R, Cn, div, do_div);
+		if (vec) transpose64_kernel<true><<<grid, block, 0, s>>>(in, out, R, Cn, div, do_div);
+		else transpose_kernel<true><<<grid, block, 0, s>>>(in, out, R, Cn, div, do_div);
 	} else {
-		dim3 grid(adc_div_up(Cn, 32), adc_div_up(R, 32));
+		dim3 grid(adc_div_up(Cn, tile), adc_div_up(R, tile));
 		if (grid.y > 65535) return ADCENSUS_ELIMIT;
-		transpose_kernel<false><<<grid, block, 0, s>>>(in, out, R, Cn, div, do_div);
+		if (vec) transpose64_kernel<false><<<grid, block, 0, s>>>(in, out, R, Cn, div, do_div);
+		else transpose_kernel<false><<<grid, block, 0, s>>>(in, out, R, Cn, div, do_div);
 	}
 	ADC_CHECK_LAUNCH();
 	return 0;
@@ -444,6 +493,16 @@ int mccnn_fill_nan(float *p, size_t n, adcensus_stream_t stream)
 		fill_nan_kernel<<<blocks, 256, 0, s>>>((float4 *)(p + head), n4, p + head + 4 * n4, tail);
 		ADC_CHECK_LAUNCH();
 	}
+	return 0;
+}
+
+int mccnn_fill_invalid(float *volL, float *volR, int D, int H, int W, adcensus_stream_t stream)
+{
+	if (!volL || !volR || D < 1 || H < 1 || W < 1) return ADCENSUS_EINVAL;
+	if (D == 1) return 0;
+	dim3 grid(8, D - 1);
+	fill_invalid_kernel<<<grid, 256, 0, adc_stream(stream)>>>(volL, volR, D, H, W);
+	ADC_CHECK_LAUNCH();
 	return 0;
 }
 

@@ -195,6 +195,18 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 		asm volatile("cp.async.commit_group;");
 	}
 
+	// penalty classes are fetched one step ahead (the row of the table changes every step of a
+	// vertical scan, so these loads miss L1; fetched just in time they were the top stall)
+	uint8_t c1n = 0, c2n[K];
+	auto fetch_classes = [&](int xs, int ys) {
+		const int ty = min(max(ys + tshift_y, 0), H - 1);   // row / column of the stored difference
+		const uint8_t *q = t2 + (long)ty * Wp + xs + tshift_x + dbase * ddir;  // D2 classes (:588-594)
+		c1n = __ldg(t1 + (long)ty * Wp + xs + tshift_x);                        // D1 class (:587)
+#pragma unroll
+		for (int k = 0; k < K; k++) c2n[k] = __ldg(q + k * ddir);
+	};
+	fetch_classes(x + dx, y + dy);                       // for step 1
+
 	float prev[K];
 	for (int s0 = 0; s0 < nsteps; s0 += PF) {
 #pragma unroll
@@ -224,9 +236,11 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 				if (lane == 0) left = adc_nan();                // d - 1 < 0 (:608)
 				if (lane == 31) right = adc_nan();
 
-				const int ty = y + tshift_y;                    // row / column of the stored difference
-				const uint8_t c1 = __ldg(t1 + (long)ty * Wp + x + tshift_x);          // D1 class (:587)
-				const uint8_t *c2p = t2 + (long)ty * Wp + x + tshift_x + dbase * ddir;  // D2 classes (:588-594)
+				const uint8_t c1 = c1n;
+				uint8_t c2[K];
+#pragma unroll
+				for (int k = 0; k < K; k++) c2[k] = c2n[k];
+				fetch_classes(x + dx, y + dy);                  // for step s + 1
 				// penalties when the D2 class equals the D1 class (both < tau or both > tau), else middle
 				const bool c1lt = c1 == 0;
 				const float P1e = c1 == 1 ? P1m : (c1lt ? P1f : P1s);
@@ -234,7 +248,7 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 				const float P1ae = c1 == 1 ? P1m_a : (c1lt ? P1f_a : P1s_a);
 #pragma unroll
 				for (int k = 0; k < K; k++) {
-					const bool eq = __ldg(c2p + k * ddir) == c1;
+					const bool eq = c2[k] == c1;
 					const float P1 = eq ? P1e : P1m, P2 = eq ? P2e : P2m, P1a = eq ? P1ae : P1m_a;
 					const float pm = k > 0 ? prev[k - 1] : left;
 					const float pp = k < K - 1 ? prev[k + 1] : right;

@@ -2,17 +2,24 @@
 //
 // Replaces adcensus.cu:1455-1498 (kernel StereoJoin_, one thread per pixel with a
 // 512-byte local-memory L cache and C*D scalar R loads).  Per image row the op is
-// a banded GEMM,  cost[d][x] = -sum_c L[c][x] * R[c][x-d],  so it is built like
-// one: a CTA owns (row y, 128 x, DC disparities), stages 8-channel slabs of the L
-// row and of the R window [x0-d0-DC, x0+128-d0) in shared memory (register
-// prefetch of the next slab overlaps the FMAs), and every thread keeps an 8x x 8d
-// accumulator tile in registers.  The R operands of a thread tile are the 15
-// consecutive columns x-d, fetched as four aligned LDS.128, so the inner loop is
-// 6 LDS.128 per 64 FFMA.  The accumulation order is the reference's (c ascending,
-// one fused multiply-add per channel into a single accumulator, adcensus.cu:1468-
-// 1471), hence results are bit-identical to it.  The finished tile is staged
-// through shared memory so that both volumes are written as full rows:
-// outL[d][y][x0..] and outR[d][y][x0-d..] are the same 128 floats.
+// a banded GEMM,  cost[x][j] = -sum_c L[c][x] * R[c][j]  for 0 <= x - j < D, and it
+// is built like one:
+//   * a CTA owns (row y, 128 columns x, a chunk of DC = 16*NS - 8 disparities).  In
+//     (x, j = x - d) space that chunk is a parallelogram; it is covered by 8x x 16j
+//     register tiles laid along the diagonal (16 x-groups, NS tiles each, 6% of the
+//     tile entries fall outside the band and are discarded), so the inner loop is a
+//     plain outer product: per channel 2 LDS.128 of L + 4 LDS.128 of R for 128 FFMA;
+//   * operands are stored in shared memory "split-plane" (the low and the high float4
+//     of every 8-float group in separate planes), which makes every quarter-warp of
+//     an LDS.128 read 128 contiguous bytes: no bank conflicts (the naive layout is
+//     2-way conflicted and was shared-memory bound at 16% FMA utilisation);
+//   * channel slabs (8 channels x [128 L | 256 R]) stream through a 3-stage cp.async
+//     ring, one barrier per slab;
+//   * accumulation is the reference's (c ascending, one fused multiply-add per
+//     channel into a single accumulator, adcensus.cu:1468-1471) => bit-identical;
+//   * the finished tile is staged through shared memory (written along tile
+//     diagonals = runs of consecutive x at fixed d) so that both volumes are written
+//     as full rows: outL[d][y][x0..] and outR[d][y][x0-d..] are the same 128 floats.
 //
 // Roofline: 2*C*H*W*4 bytes read + 2*valid*4 bytes written (valid = H*(D*W -
 // D(D-1)/2)); at C=64 the FMA work (2*C flop per output) sits at the fp32 ridge
@@ -21,152 +28,176 @@
 
 namespace {
 
-constexpr int SJ_TX = 128;   // x per CTA
-constexpr int SJ_CCH = 8;    // channels per shared-memory stage
-constexpr int SJ_OPITCH = SJ_TX + 4;
+constexpr int SJ_TX = 128;      // x per CTA (16 groups of 8)
+constexpr int SJ_CCH = 8;       // channels per pipeline stage
+constexpr int SJ_NSTAGE = 3;
+constexpr int SJ_ROW = SJ_TX + 2 * SJ_TX;   // floats per channel row: [L 128][R 256]
 
-template <int DC>
+template <int NS>
 struct SJCfg {
-	static constexpr int NT = 2 * DC;            // threads: 16 x-groups * (DC/8) d-groups
-	static constexpr int ROWW = SJ_TX + SJ_TX + DC;  // [L: 128][R window: 128 + DC]
-	static constexpr int NSLOT = (ROWW + NT - 1) / NT;
-	static constexpr int STAGE = SJ_CCH * ROWW;  // floats per stage
-	static constexpr int SMEM_PIPE = 2 * STAGE * 4;
-	static constexpr int SMEM_OUT = DC * SJ_OPITCH * 4;
+	static constexpr int DC = 16 * NS - 8;          // disparities per CTA
+	static constexpr int NT = 16 * NS;              // threads
+	static constexpr int STAGE = SJ_CCH * SJ_ROW;   // floats
+	static constexpr int SMEM_PIPE = SJ_NSTAGE * STAGE * 4;
+	static constexpr int SMEM_OUT = DC * SJ_TX * 4;
 	static constexpr int SMEM = SMEM_PIPE > SMEM_OUT ? SMEM_PIPE : SMEM_OUT;
 };
 
-template <int DC>
-__global__ void __launch_bounds__(2 * DC, (DC >= 128) ? 2 : 3)
+// split-plane position of element i of a row of NG 8-float groups
+__device__ __forceinline__ int split_pos(int i, int NG) { return ((i & 7) >> 2) * (NG * 4) + (i >> 3) * 4 + (i & 3); }
+
+template <int NS>
+__global__ void __launch_bounds__(16 * NS, (NS >= 6) ? 3 : 4)
 stereo_join_kernel(const float *__restrict__ gL, const float *__restrict__ gR,
 		   float *__restrict__ outL, float *__restrict__ outR,
 		   int C, int D, int H, int W)
 {
-	using Cfg = SJCfg<DC>;
+	using Cfg = SJCfg<NS>;
+	constexpr int DC = Cfg::DC, NT = Cfg::NT;
 	extern __shared__ __align__(16) float smem[];
 
 	const int tid = threadIdx.x;
-	const int lane = tid & 31, warp = tid >> 5;
-	const int tx = 8 * (warp & 1) + (lane & 7);   // 0..15 : x group (8 columns each)
-	const int td = 4 * (warp >> 1) + (lane >> 3); // 0..DC/8-1 : d group (8 disparities each)
+	const int gx = (tid & 7) + 8 * ((tid >> 3) & 1);    // x group (8 columns); a quarter-warp = 8 consecutive groups
+	const int s = tid >> 4;                              // tile index along the diagonal, 0..NS-1
 	const int X0 = blockIdx.x * SJ_TX;
 	const int y = blockIdx.y;
 	const int d0 = blockIdx.z * DC;
 	const long HW = (long)H * W;
-	const int jbase = X0 - d0 - DC;               // image column of R-window slot 0
+	const int jbase = X0 - d0 - (DC - 1);                // image column of R-window slot 0
 
-	// ---- per-thread fill slots: column `col` of the stage row, fixed for the whole kernel
-	const float *src[Cfg::NSLOT];
-	bool ok[Cfg::NSLOT];
+	// ---- fill slots: 3 fixed columns of the channel row per thread ---------------------------
+	constexpr int NSLOT = (SJ_ROW + NT - 1) / NT;
+	const float *src[NSLOT];
+	int dst[NSLOT];
+	bool ok[NSLOT];
 #pragma unroll
-	for (int m = 0; m < Cfg::NSLOT; m++) {
-		int col = tid + m * Cfg::NT;
-		bool isL = col < SJ_TX;
-		int xc = isL ? X0 + col : jbase + (col - SJ_TX);
-		ok[m] = col < Cfg::ROWW && xc >= 0 && xc < W;
+	for (int m = 0; m < NSLOT; m++) {
+		const int col = tid + m * NT;
+		const bool isL = col < SJ_TX;
+		const int li = isL ? col : col - SJ_TX;          // logical index inside the L row / R window
+		const int xc = isL ? X0 + li : jbase + li;       // image column
+		ok[m] = col < SJ_ROW && xc >= 0 && xc < W;
 		src[m] = (isL ? gL : gR) + (long)y * W + (ok[m] ? xc : 0);
+		dst[m] = col < SJ_ROW ? (isL ? split_pos(li, 16) : SJ_TX + split_pos(li, 32)) : -1;
 	}
-
-	float pre[SJ_CCH][Cfg::NSLOT];
-	auto prefetch = [&](int c0) {
+	auto issue_stage = [&](int stage_idx, int buf) {
+		float *sb = smem + buf * Cfg::STAGE;
+		const int c0 = stage_idx * SJ_CCH;
 #pragma unroll
-		for (int cc = 0; cc < SJ_CCH; cc++)
+		for (int cc = 0; cc < SJ_CCH; cc++) {
+			const bool cok = c0 + cc < C;
 #pragma unroll
-			for (int m = 0; m < Cfg::NSLOT; m++) {
-				bool p = ok[m] && (c0 + cc < C);
-				pre[cc][m] = p ? __ldg(src[m] + (long)(c0 + cc) * HW) : 0.0f;
+			for (int m = 0; m < NSLOT; m++) {
+				if (dst[m] >= 0) {
+					const unsigned sa = (unsigned)__cvta_generic_to_shared(sb + cc * SJ_ROW + dst[m]);
+					const int nbytes = (ok[m] && cok) ? 4 : 0;   // zero-fill outside the image / beyond C
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa),
+						     "l"(src[m] + (long)(cok ? c0 + cc : 0) * HW), "r"(nbytes));
+				}
 			}
-	};
-	auto commit = [&](float *stage) {
-#pragma unroll
-		for (int cc = 0; cc < SJ_CCH; cc++)
-#pragma unroll
-			for (int m = 0; m < Cfg::NSLOT; m++) {
-				int col = tid + m * Cfg::NT;
-				if (col < Cfg::ROWW) stage[cc * Cfg::ROWW + col] = pre[cc][m];
-			}
+		}
 	};
 
-	float acc[8][8];
+	float acc[8][16];
 #pragma unroll
 	for (int i = 0; i < 8; i++)
 #pragma unroll
-		for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+		for (int j = 0; j < 16; j++) acc[i][j] = 0.0f;
 
-	// this thread's operand segments inside a stage row
-	const int lofs = 8 * tx;
-	const int rofs = SJ_TX + 8 * (tx - td) + DC - 8;   // 16 floats; r[8 + xi - di] pairs with (xi, di)
-	const bool active = d0 + 8 * td < D;               // whole d-group beyond D: nothing to compute
+	// this tile's disparities: d - d0 = DC-1 - 16 s + xi - ji
+	const int dtop = d0 + (DC - 1) - 16 * s;             // d at (xi - ji) = 0
+	const bool active = (dtop - 15 < D) && (dtop - 15 < d0 + DC) && (dtop + 7 >= d0);
+	const int lofs = gx * 4;                             // float4 slot of this x group in the L planes
+	const int rofs = SJ_TX + (gx + 2 * s) * 4;           // first 8-float group of the 16 R columns
 
 	const int nstage = (C + SJ_CCH - 1) / SJ_CCH;
-	prefetch(0);
-	commit(smem);
-	__syncthreads();
-	for (int s = 0; s < nstage; s++) {
-		float *cur = smem + (s & 1) * Cfg::STAGE;
-		float *nxt = smem + ((s + 1) & 1) * Cfg::STAGE;
-		if (s + 1 < nstage) prefetch((s + 1) * SJ_CCH);
+#pragma unroll
+	for (int p = 0; p < SJ_NSTAGE - 1; p++) {
+		if (p < nstage) issue_stage(p, p);
+		asm volatile("cp.async.commit_group;");
+	}
+	for (int st = 0; st < nstage; st++) {
+		asm volatile("cp.async.wait_group %0;" ::"n"(SJ_NSTAGE - 2));
+		__syncthreads();                                 // slab st visible; slab st-1's buffer free
+		if (st + SJ_NSTAGE - 1 < nstage) issue_stage(st + SJ_NSTAGE - 1, (st + SJ_NSTAGE - 1) % SJ_NSTAGE);
+		asm volatile("cp.async.commit_group;");
 		if (active) {
+			const float *sb = smem + (st % SJ_NSTAGE) * Cfg::STAGE;
 #pragma unroll
 			for (int cc = 0; cc < SJ_CCH; cc++) {
-				const float *row = cur + cc * Cfg::ROWW;
+				const float *row = sb + cc * SJ_ROW;
 				float l[8], r[16];
 				*reinterpret_cast<float4 *>(&l[0]) = *reinterpret_cast<const float4 *>(row + lofs);
-				*reinterpret_cast<float4 *>(&l[4]) = *reinterpret_cast<const float4 *>(row + lofs + 4);
-#pragma unroll
-				for (int k = 0; k < 4; k++)
-					*reinterpret_cast<float4 *>(&r[4 * k]) = *reinterpret_cast<const float4 *>(row + rofs + 4 * k);
+				*reinterpret_cast<float4 *>(&l[4]) = *reinterpret_cast<const float4 *>(row + 64 + lofs);
+				*reinterpret_cast<float4 *>(&r[0]) = *reinterpret_cast<const float4 *>(row + rofs);
+				*reinterpret_cast<float4 *>(&r[4]) = *reinterpret_cast<const float4 *>(row + 128 + rofs);
+				*reinterpret_cast<float4 *>(&r[8]) = *reinterpret_cast<const float4 *>(row + rofs + 4);
+				*reinterpret_cast<float4 *>(&r[12]) = *reinterpret_cast<const float4 *>(row + 128 + rofs + 4);
 #pragma unroll
 				for (int xi = 0; xi < 8; xi++)
 #pragma unroll
-					for (int di = 0; di < 8; di++)
-						acc[xi][di] = fmaf(-l[xi], r[8 + xi - di], acc[xi][di]); // adcensus.cu:1470
+					for (int ji = 0; ji < 16; ji++)
+						acc[xi][ji] = fmaf(-l[xi], r[ji], acc[xi][ji]);  // adcensus.cu:1470
 			}
 		}
-		if (s + 1 < nstage) commit(nxt);
-		__syncthreads();
 	}
+	asm volatile("cp.async.wait_group 0;");
+	__syncthreads();                                     // pipeline buffers are reused as the output stage
 
-	// ---- epilogue: stage the DC x 128 tile, then write full rows of both volumes
+	// ---- epilogue 1: tile diagonals (fixed d, consecutive x) -> so[dd][split(x)] -------------
 	float *so = smem;
 #pragma unroll
-	for (int di = 0; di < 8; di++) {
-		float *p = so + (8 * td + di) * SJ_OPITCH + 8 * tx;
-		*reinterpret_cast<float4 *>(p) = make_float4(acc[0][di], acc[1][di], acc[2][di], acc[3][di]);
-		*reinterpret_cast<float4 *>(p + 4) = make_float4(acc[4][di], acc[5][di], acc[6][di], acc[7][di]);
+	for (int t = -15; t <= 7; t++) {                     // t = xi - ji
+		const int dd = (DC - 1) - 16 * s + t;            // d - d0
+		if (dd < 0 || dd >= DC) continue;
+		float *rowp = so + dd * SJ_TX + gx * 4;
+#pragma unroll
+		for (int h = 0; h < 2; h++) {                    // halves xi = 4h .. 4h+3
+			const bool full = (4 * h - t >= 0) && (4 * h + 3 - t <= 15);
+			if (full) {
+				*reinterpret_cast<float4 *>(rowp + h * 64) =
+					make_float4(acc[4 * h][4 * h - t], acc[4 * h + 1][4 * h + 1 - t],
+						    acc[4 * h + 2][4 * h + 2 - t], acc[4 * h + 3][4 * h + 3 - t]);
+			} else {
+#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const int xi = 4 * h + e, ji = xi - t;
+					if (ji >= 0 && ji <= 15) rowp[h * 64 + e] = acc[xi][ji];
+				}
+			}
+		}
 	}
 	__syncthreads();
-	constexpr int NW = Cfg::NT / 32;
-	for (int r = warp; r < DC; r += NW) {
-		int d = d0 + r;
-		if (d >= D) break;
-		long rowbase = (long)d * HW + (long)y * W;
-#pragma unroll
-		for (int k = 0; k < SJ_TX / 32; k++) {
-			int xl = lane + 32 * k;
-			int x = X0 + xl;
-			if (x < W && x >= d) {
-				float v = so[r * SJ_OPITCH + xl];
-				outL[rowbase + x] = v;       // adcensus.cu:1472
-				outR[rowbase + x - d] = v;   // adcensus.cu:1473
-			}
+
+	// ---- epilogue 2: full rows of both volumes ------------------------------------------------
+	// (NT need not be a multiple of 32: index by thread, consecutive threads -> consecutive x)
+	const int nrows = min(DC, D - d0);
+	for (int idx = tid; idx < nrows * SJ_TX; idx += NT) {
+		const int r = idx >> 7, xl = idx & (SJ_TX - 1);
+		const int d = d0 + r;
+		const int x = X0 + xl;
+		if (x < W && x >= d) {
+			const float v = so[r * SJ_TX + split_pos(xl, 16)];
+			const long rowbase = (long)d * HW + (long)y * W;
+			outL[rowbase + x] = v;       // adcensus.cu:1472
+			outR[rowbase + x - d] = v;   // adcensus.cu:1473
 		}
 	}
 }
 
-template <int DC>
+template <int NS>
 int launch(const float *L, const float *R, float *outL, float *outR, int C, int D, int H, int W, cudaStream_t s)
 {
-	using Cfg = SJCfg<DC>;
+	using Cfg = SJCfg<NS>;
 	static bool attr_done[64] = {false};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!attr_done[dev & 63]) {
-		ADC_CUDA(cudaFuncSetAttribute(stereo_join_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+		ADC_CUDA(cudaFuncSetAttribute(stereo_join_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
 		attr_done[dev & 63] = true;
 	}
-	dim3 grid(adc_div_up(W, SJ_TX), H, adc_div_up(D, DC));
-	stereo_join_kernel<DC><<<grid, Cfg::NT, Cfg::SMEM, s>>>(L, R, outL, outR, C, D, H, W);
+	dim3 grid(adc_div_up(W, SJ_TX), H, adc_div_up(D, Cfg::DC));
+	stereo_join_kernel<NS><<<grid, Cfg::NT, Cfg::SMEM, s>>>(L, R, outL, outR, C, D, H, W);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
@@ -180,12 +211,18 @@ extern "C" int adcensus_StereoJoin(const float *input_L, const float *input_R, f
 	if (C < 1 || D < 1 || H < 1 || W < 1 || H > 65535) return ADCENSUS_EINVAL;
 	if (C > 128) return ADCENSUS_ELIMIT;  // reference: float L_cache[128] (adcensus.cu:1460-1461)
 	cudaStream_t s = adc_stream(stream);
-	int nchunk = adc_div_up(D, 128);
-	int dc = adc_div_up(adc_div_up(D, nchunk), 32) * 32;
-	switch (dc) {
-	case 32: return launch<32>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	case 64: return launch<64>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	case 96: return launch<96>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	default: return launch<128>(input_L, input_R, output_L, output_R, C, D, H, W, s);
+	// split D into equal chunks of at most 120 and pick the smallest tile count that covers one
+	const int nchunk = adc_div_up(D, 120);
+	const int dc = adc_div_up(D, nchunk);
+	const int ns = adc_div_up(dc + 8, 16);
+	switch (ns) {
+	case 1: return launch<1>(input_L, input_R, output_L, output_R, C, D, H, W, s);
+	case 2: return launch<2>(input_L, input_R, output_L, output_R, C, D, H, W, s);
+	case 3: return launch<3>(input_L, input_R, output_L, output_R, C, D, H, W, s);
+	case 4: return launch<4>(input_L, input_R, output_L, output_R, C, D, H, W, s);
+	case 5: return launch<5>(input_L, input_R, output_L, output_R, C, D, H, W, s);
+	case 6: return launch<6>(input_L, input_R, output_L, output_R, C, D, H, W, s);
+	case 7: return launch<7>(input_L, input_R, output_L, output_R, C, D, H, W, s);
+	default: return launch<8>(input_L, input_R, output_L, output_R, C, D, H, W, s);
 	}
 }

@@ -209,7 +209,12 @@ int luaL_error(lua_State *, const char *fmt, ...)
 void luaL_openlib(lua_State *, const char *libname, const luaL_Reg *l, int)
 {
 	std::vector<luaL_Reg> &v = registry()[libname];
-	for (; l && l->name; l++) v.push_back(*l);
+	for (; l && l->name; l++) {
+		bool found = false;
+		for (luaL_Reg &r : v)
+			if (strcmp(r.name, l->name) == 0) { r.func = l->func; found = true; }  /* re-open: replace */
+		if (!found) v.push_back(*l);
+	}
 }
 
 /* ---- luaT ------------------------------------------------------------ */
