@@ -68,6 +68,15 @@ int adcensus_cbca(const float *x0c, const float *x1c, const float *vol_in, float
 int adcensus_cbca_ex(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 		     int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream);
 
+/* The two halves of adcensus_cbca for callers that aggregate several times with the same arms
+ * (main.lua runs cbca_i1 + cbca_i2 iterations per direction): pack both arm tensors once into
+ * `packed` (mccnn_packed_arms_bytes(H, W) bytes of device memory), then iterate.  x0c/x1c are still
+ * passed to the aggregation for the generic kernel that serves arms longer than 14 pixels. */
+size_t mccnn_packed_arms_bytes(int H, int W);
+int mccnn_pack_arms(const float *x0c, const float *x1c, void *packed, int H, int W, adcensus_stream_t stream);
+int mccnn_cbca_packed(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+		      int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream);
+
 /* adcensus.sgm2(x0, x1, input, output, tmp, pi1, pi2, tau_so, alpha1, sgm_q1,
  *               sgm_q2, direction)  adcensus.cu:535-697
  * input/output are (H,W,D); output is accumulated into (+=) in the order right,
@@ -172,6 +181,14 @@ int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const float *featR
  * copies disp back, and returns after the result is in disp_host. */
 int mccnn_pipeline_run_host(mccnn_pipeline *p, const float *featL_host, const float *featR_host,
 			    const float *imgL_host, const float *imgR_host, float *disp_host);
+
+/* Same for n pairs (arrays of n host pointers each): the H2D copy of pair i+1 and the D2H copy of
+ * pair i-1 overlap the kernels of pair i (two staging slots, a copy stream and a compute stream).
+ * Host buffers should be pinned for the overlap to materialise.  Returns when all n results are
+ * in their host buffers. */
+int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const float *const *featL_host,
+				  const float *const *featR_host, const float *const *imgL_host,
+				  const float *const *imgR_host, float *const *disp_host);
 
 #ifdef __cplusplus
 }

@@ -132,7 +132,7 @@ __device__ __forceinline__ void row_taps<1>(float &acc, int &cnt, const float *w
 }
 
 template <int R>
-__global__ void __launch_bounds__(CW_NT)
+__global__ void __launch_bounds__(CW_NT, 4)
 cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
 		const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction)
 {
@@ -174,6 +174,20 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 		const int d = d0 + dd;
 		const float *plane = vol + (long)d * HW;
 		const int off = (x0 + d * direction) - a1x0;   // sa1 column of tile column 0
+		// whole tile inside the invalid triangle (x + d*direction outside the image for every
+		// column): plain copy, adcensus.cu:353-354 (CTA-uniform, so no barrier is skipped unevenly)
+		if (direction < 0 ? (x0 + CW_TX - 1 - d < 0) : (x0 + d >= W)) {
+#pragma unroll
+			for (int oy = 0; oy < 2; oy++) {
+				const int y = y0 + ry + oy;
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const int x = x0 + cx + j;
+					if (y < H && x < W) out[(long)d * HW + (long)y * W + x] = __ldg(plane + (long)y * W + x);
+				}
+			}
+			continue;
+		}
 		__syncthreads();                               // previous plane consumed; arms visible
 		// volume plane tile (+halo): cp.async, 4-byte granules (rows of W floats are only 4-byte
 		// aligned), zero-filled outside the image
@@ -428,6 +442,32 @@ int adc_cbca_packed(const uint32_t *a0, const uint32_t *a1, const float *x0c, co
 	}
 	ADC_CHECK_LAUNCH();
 	return 0;
+}
+
+// Public split of adcensus_cbca for callers that aggregate several times with the same arms (main.lua
+// runs cbca_i1 + cbca_i2 iterations per direction): pack both arm tensors once, then iterate.
+extern "C" int mccnn_pack_arms(const float *x0c, const float *x1c, void *packed, int H, int W, adcensus_stream_t stream)
+{
+	if (!x0c || !x1c || !packed || H < 1 || W < 1) return ADCENSUS_EINVAL;
+	cudaStream_t s = adc_stream(stream);
+	uint32_t *pk = (uint32_t *)packed;
+	const long HW = (long)H * W;
+	int *maxlen_dev = (int *)(pk + 2 * HW);
+	int rc = (int)cudaMemsetAsync(maxlen_dev, 0, sizeof(int), s);
+	if (!rc) rc = adc_pack_arms(x0c, pk, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_pack_arms(x1c, pk + HW, H, W, maxlen_dev, s);
+	return rc;
+}
+
+extern "C" size_t mccnn_packed_arms_bytes(int H, int W) { return (2 * (size_t)H * W + 1) * sizeof(uint32_t); }
+
+extern "C" int mccnn_cbca_packed(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+				 int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream)
+{
+	if (!packed || !x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
+	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1) || max_arm < 1) return ADCENSUS_EINVAL;
+	const uint32_t *pk = (const uint32_t *)packed;
+	return adc_cbca_packed(pk, pk + (long)H * W, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, adc_stream(stream));
 }
 
 extern "C" int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1, adcensus_stream_t stream)

@@ -39,9 +39,11 @@ struct mccnn_pipeline {
 	float *gauss;     // ks*ks
 	uint8_t *sgmtab;  // SGM penalty-class tables
 	int ks;
-	// staging for the host-buffer entry point
-	float *h_feat, *h_img, *h_disp;  // device copies: 2F, 2HW, HW
-	cudaStream_t own_stream;
+	// staging for the host-buffer entry points: two slots so that the copy of pair i+1 overlaps
+	// the kernels of pair i
+	float *h_feat[2], *h_img[2], *h_disp[2];  // device copies per slot: 2F, 2HW, HW
+	cudaStream_t own_stream, copy_stream, out_stream;
+	cudaEvent_t ev_in[2], ev_free[2], ev_out[2];
 };
 
 namespace {
@@ -109,8 +111,15 @@ extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
 	DeviceGuard g(p->device);
 	cudaFree(p->vols); cudaFree(p->bufA); cudaFree(p->bufC); cudaFree(p->x0c); cudaFree(p->x1c);
 	cudaFree(p->packed); cudaFree(p->maxlen); cudaFree(p->maps); cudaFree(p->gauss); cudaFree(p->sgmtab);
-	cudaFree(p->h_feat); cudaFree(p->h_img); cudaFree(p->h_disp);
+	for (int k = 0; k < 2; k++) {
+		cudaFree(p->h_feat[k]); cudaFree(p->h_img[k]); cudaFree(p->h_disp[k]);
+		if (p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
+		if (p->ev_free[k]) cudaEventDestroy(p->ev_free[k]);
+		if (p->ev_out[k]) cudaEventDestroy(p->ev_out[k]);
+	}
 	if (p->own_stream) cudaStreamDestroy(p->own_stream);
+	if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+	if (p->out_stream) cudaStreamDestroy(p->out_stream);
 	delete p;
 }
 
@@ -196,29 +205,66 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 	return 0;
 }
 
+static int host_staging(mccnn_pipeline *p)
+{
+	if (p->own_stream) return 0;
+	const size_t F = (size_t)p->C * p->HW * sizeof(float), I = (size_t)p->HW * sizeof(float);
+	int rc = 0;
+	for (int k = 0; k < 2 && !rc; k++) {
+		if (!rc) rc = dev_alloc((void **)&p->h_feat[k], 2 * F, &p->bytes);
+		if (!rc) rc = dev_alloc((void **)&p->h_img[k], 2 * I, &p->bytes);
+		if (!rc) rc = dev_alloc((void **)&p->h_disp[k], I, &p->bytes);
+		if (!rc) rc = (int)cudaEventCreateWithFlags(&p->ev_in[k], cudaEventDisableTiming);
+		if (!rc) rc = (int)cudaEventCreateWithFlags(&p->ev_free[k], cudaEventDisableTiming);
+		if (!rc) rc = (int)cudaEventCreateWithFlags(&p->ev_out[k], cudaEventDisableTiming);
+	}
+	if (!rc) rc = (int)cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
+	if (!rc) rc = (int)cudaStreamCreateWithFlags(&p->out_stream, cudaStreamNonBlocking);
+	if (!rc) rc = (int)cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+	return rc;
+}
+
+// n pairs from host memory (pinned for real overlap): pair i's inputs are copied on a copy stream
+// into staging slot i%2 while pair i-1 computes; its disparity map is copied back on the copy
+// stream while pair i+1 computes (separate H2D / kernel / D2H streams, two staging slots).
+// Returns when every result is in its host buffer.
+extern "C" int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const float *const *featL_host,
+					     const float *const *featR_host, const float *const *imgL_host,
+					     const float *const *imgR_host, float *const *disp_host)
+{
+	if (!p || n < 0 || (n > 0 && (!featL_host || !featR_host || !imgL_host || !imgR_host || !disp_host))) return ADCENSUS_EINVAL;
+	for (int i = 0; i < n; i++)
+		if (!featL_host[i] || !featR_host[i] || !imgL_host[i] || !imgR_host[i] || !disp_host[i]) return ADCENSUS_EINVAL;
+	DeviceGuard g(p->device);
+	STEP(host_staging(p));
+	const size_t F = (size_t)p->C * p->HW * sizeof(float), I = (size_t)p->HW * sizeof(float);
+	cudaStream_t cs = p->copy_stream, ks = p->own_stream, os = p->out_stream;  // H2D, kernels, D2H
+	for (int i = 0; i < n; i++) {
+		const int k = i & 1;
+		float *fL = p->h_feat[k], *fR = fL + (size_t)p->C * p->HW;
+		float *iL = p->h_img[k], *iR = iL + p->HW;
+		if (i >= 2) ADC_CUDA(cudaStreamWaitEvent(cs, p->ev_free[k], 0));   // slot's previous pair consumed
+		ADC_CUDA(cudaMemcpyAsync(fL, featL_host[i], F, cudaMemcpyHostToDevice, cs));
+		ADC_CUDA(cudaMemcpyAsync(fR, featR_host[i], F, cudaMemcpyHostToDevice, cs));
+		ADC_CUDA(cudaMemcpyAsync(iL, imgL_host[i], I, cudaMemcpyHostToDevice, cs));
+		ADC_CUDA(cudaMemcpyAsync(iR, imgR_host[i], I, cudaMemcpyHostToDevice, cs));
+		ADC_CUDA(cudaEventRecord(p->ev_in[k], cs));
+		ADC_CUDA(cudaStreamWaitEvent(ks, p->ev_in[k], 0));
+		if (i >= 2) ADC_CUDA(cudaStreamWaitEvent(ks, p->ev_out[k], 0));     // slot's previous result copied out
+		STEP(mccnn_pipeline_run(p, fL, fR, iL, iR, p->h_disp[k], nullptr, nullptr, ks));
+		ADC_CUDA(cudaEventRecord(p->ev_free[k], ks));
+		ADC_CUDA(cudaStreamWaitEvent(os, p->ev_free[k], 0));
+		ADC_CUDA(cudaMemcpyAsync(disp_host[i], p->h_disp[k], I, cudaMemcpyDeviceToHost, os));
+		ADC_CUDA(cudaEventRecord(p->ev_out[k], os));
+	}
+	ADC_CUDA(cudaStreamSynchronize(os));
+	ADC_CUDA(cudaStreamSynchronize(ks));
+	ADC_CUDA(cudaStreamSynchronize(cs));
+	return 0;
+}
+
 extern "C" int mccnn_pipeline_run_host(mccnn_pipeline *p, const float *featL_host, const float *featR_host,
 				       const float *imgL_host, const float *imgR_host, float *disp_host)
 {
-	if (!p || !featL_host || !featR_host || !imgL_host || !imgR_host || !disp_host) return ADCENSUS_EINVAL;
-	DeviceGuard g(p->device);
-	const size_t F = (size_t)p->C * p->HW * sizeof(float), I = (size_t)p->HW * sizeof(float);
-	if (!p->h_feat) {
-		int rc = 0;
-		if (!rc) rc = dev_alloc((void **)&p->h_feat, 2 * F, &p->bytes);
-		if (!rc) rc = dev_alloc((void **)&p->h_img, 2 * I, &p->bytes);
-		if (!rc) rc = dev_alloc((void **)&p->h_disp, I, &p->bytes);
-		if (!rc) rc = (int)cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
-		if (rc) return rc;
-	}
-	cudaStream_t s = p->own_stream;
-	float *fL = p->h_feat, *fR = p->h_feat + (size_t)p->C * p->HW;
-	float *iL = p->h_img, *iR = p->h_img + p->HW;
-	ADC_CUDA(cudaMemcpyAsync(fL, featL_host, F, cudaMemcpyHostToDevice, s));
-	ADC_CUDA(cudaMemcpyAsync(fR, featR_host, F, cudaMemcpyHostToDevice, s));
-	ADC_CUDA(cudaMemcpyAsync(iL, imgL_host, I, cudaMemcpyHostToDevice, s));
-	ADC_CUDA(cudaMemcpyAsync(iR, imgR_host, I, cudaMemcpyHostToDevice, s));
-	STEP(mccnn_pipeline_run(p, fL, fR, iL, iR, p->h_disp, nullptr, nullptr, s));
-	ADC_CUDA(cudaMemcpyAsync(disp_host, p->h_disp, I, cudaMemcpyDeviceToHost, s));
-	ADC_CUDA(cudaStreamSynchronize(s));
-	return 0;
+	return mccnn_pipeline_run_host_batch(p, 1, &featL_host, &featR_host, &imgL_host, &imgR_host, &disp_host);
 }

@@ -78,6 +78,36 @@ __global__ void interp_occ_kernel(const float *__restrict__ d0, const float *__r
 	out[id] = (x + dx < W) ? d0[id + dx] : d0[id];
 }
 
+// Row form of the same rule (adcensus.cu:1087-1103): instead of every occluded pixel walking its
+// row, one block per row records for every column the nearest label-0 pixel to the left and to the
+// right (two serial scans over shared memory by two warps), then all threads pick left-else-right.
+__global__ void interp_occ_row_kernel(const float *__restrict__ d0, const float *__restrict__ outlier, float *__restrict__ out, int W)
+{
+	extern __shared__ int occ_smem[];
+	int *nl = occ_smem;          // nearest match at or left of x, else -1
+	int *nr = occ_smem + W;      // nearest match at or right of x, else W
+	float *lab = reinterpret_cast<float *>(occ_smem + 2 * W);
+	const long row = (long)blockIdx.x * W;
+	for (int x = threadIdx.x; x < W; x += blockDim.x) lab[x] = outlier[row + x];
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int last = -1;
+		for (int x = 0; x < W; x++) { last = lab[x] == 0.0f ? x : last; nl[x] = last; }
+	} else if (threadIdx.x == 32) {
+		int last = W;
+		for (int x = W - 1; x >= 0; x--) { last = lab[x] == 0.0f ? x : last; nr[x] = last; }
+	}
+	__syncthreads();
+	for (int x = threadIdx.x; x < W; x += blockDim.x) {
+		float v = d0[row + x];
+		if (lab[x] == 1.0f) {
+			if (nl[x] >= 0) v = d0[row + nl[x]];          // :1090-1092 found walking left
+			else if (nr[x] < W) v = d0[row + nr[x]];      // :1093-1098 else walking right
+		}
+		out[row + x] = v;
+	}
+}
+
 __device__ __forceinline__ void sel_sort(float *v, int n)           // adcensus.cu:47-60
 {
 	for (int i = 0; i < n - 1; i++) {
@@ -198,6 +228,49 @@ __global__ void mean2d_kernel(const float *__restrict__ img, const float *__rest
 		}
 	}
 	out[id] = sum / cnt;
+}
+
+// Shared-memory form of the same filter: a 32x8 pixel tile plus a halo of r is staged once (NaN
+// outside the image: |NaN - c| < alpha2 is false, so those taps drop out exactly like the
+// reference's bounds test), the (2r+1)^2 weights too; the tap loop then has no bounds checks and
+// keeps the reference's order (x outer, y inner, adcensus.cu:1251-1252) and its fused multiply-add.
+constexpr int M2_TX = 32, M2_TY = 8;
+__global__ void __launch_bounds__(M2_TX * M2_TY)
+mean2d_tile_kernel(const float *__restrict__ img, const float *__restrict__ kernel, float *__restrict__ out,
+		   int r, int H, int W, float alpha2)
+{
+	extern __shared__ float m2_smem[];
+	const int ks = 2 * r + 1;
+	const int TW = M2_TX + 2 * r, TH = M2_TY + 2 * r;
+	float *tile = m2_smem;                  // [TH][TW]
+	float *wts = m2_smem + TH * TW;         // [ks][ks], index (dx + r) * ks + (dy + r)
+	const int tid = threadIdx.y * M2_TX + threadIdx.x;
+	const int x0 = blockIdx.x * M2_TX, y0 = blockIdx.y * M2_TY;
+	for (int i = tid; i < TH * TW; i += M2_TX * M2_TY) {
+		int ty = i / TW, tx = i - ty * TW;
+		int yy = y0 - r + ty, xx = x0 - r + tx;
+		tile[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + yy * W + xx) : adc_nan();
+	}
+	for (int i = tid; i < ks * ks; i += M2_TX * M2_TY) wts[i] = __ldg(kernel + i);
+	__syncthreads();
+	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+	if (x >= W || y >= H) return;
+	const float c = tile[(threadIdx.y + r) * TW + threadIdx.x + r];
+	float sum = 0.0f, cnt = 0.0f;
+	for (int dxx = 0; dxx < ks; dxx++) {                             // :1251 (x outer)
+		const float *col = tile + threadIdx.y * TW + threadIdx.x + dxx;
+		const float *wcol = wts + dxx * ks;
+#pragma unroll 4
+		for (int dyy = 0; dyy < ks; dyy++) {
+			const float q = col[dyy * TW];
+			if (fabsf(q - c) < alpha2) {                             // :1253
+				const float w = wcol[dyy];
+				sum = fmaf(q, w, sum);                               // :1254
+				cnt += w;                                            // :1255
+			}
+		}
+	}
+	out[y * W + x] = sum / cnt;
 }
 
 // ------------------------------------------------------------------ Normalize
@@ -413,7 +486,13 @@ int adcensus_outlier_detection(const float *d0, const float *d1, float *outlier,
 int adcensus_interpolate_occlusion(const float *d0, const float *outlier, float *out, int H, int W, adcensus_stream_t stream)
 {
 	if (!d0 || !outlier || !out || H < 1 || W < 1) return ADCENSUS_EINVAL;
-	LAUNCH1D(interp_occ_kernel, H * W, adc_stream(stream), d0, outlier, out, H * W, W);
+	const size_t smem = 3 * (size_t)W * sizeof(int);
+	if (smem <= 48 * 1024) {
+		interp_occ_row_kernel<<<H, 128, smem, adc_stream(stream)>>>(d0, outlier, out, W);
+		ADC_CHECK_LAUNCH();
+	} else {
+		LAUNCH1D(interp_occ_kernel, H * W, adc_stream(stream), d0, outlier, out, H * W, W);
+	}
 	return 0;
 }
 
@@ -443,7 +522,18 @@ int adcensus_median2d(const float *img, float *out, int H, int W, int kernel_siz
 int adcensus_mean2d(const float *img, const float *kernel, float *out, int H, int W, int ksize, float alpha2, adcensus_stream_t stream)
 {
 	if (!img || !kernel || !out || H < 1 || W < 1 || ksize < 1 || ksize % 2 != 1) return ADCENSUS_EINVAL;  // :1269
-	LAUNCH1D(mean2d_kernel, H * W, adc_stream(stream), img, kernel, out, H * W, ksize / 2, H, W, alpha2);
+	const int r = ksize / 2;
+	const size_t smem = ((size_t)(M2_TY + 2 * r) * (M2_TX + 2 * r) + (size_t)ksize * ksize) * sizeof(float);
+	if (smem <= 200 * 1024) {
+		if (smem > 48 * 1024) {
+			ADC_CUDA(cudaFuncSetAttribute(mean2d_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		}
+		dim3 grid(adc_div_up(W, M2_TX), adc_div_up(H, M2_TY)), block(M2_TX, M2_TY);
+		mean2d_tile_kernel<<<grid, block, smem, adc_stream(stream)>>>(img, kernel, out, r, H, W, alpha2);
+		ADC_CHECK_LAUNCH();
+	} else {
+		LAUNCH1D(mean2d_kernel, H * W, adc_stream(stream), img, kernel, out, H * W, r, H, W, alpha2);
+	}
 	return 0;
 }
 

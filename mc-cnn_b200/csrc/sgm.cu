@@ -82,7 +82,7 @@ __global__ void sgm_class_kernel(const float *__restrict__ x0, const float *__re
 __device__ __forceinline__ float warp_min_f32(float v)
 {
 	float r;
-	asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));  // NaN inputs are skipped
+	asm("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));  // NaN inputs are skipped
 	return r;
 }
 
@@ -140,7 +140,10 @@ __device__ __forceinline__ void store_vec(const float (&r)[K], float *p, int dba
 
 // ---------------------------------------------------------------- one scan direction
 // SD: 0 right, 1 left, 2 down, 3 up (adcensus.cu:541-565).  ZERO: output known to be 0 on entry.
-template <int K, bool VEC, int SD, bool ZERO, int PF, int WPB>
+// NR: scanlines per warp.  A horizontal scan has only H (370) lines of W (1226) strictly serial
+// steps, one warp per SM sub-partition; interleaving NR = 2 independent lines in one warp fills the
+// dependent-issue bubbles of the recurrence (min tree -> CREDUX -> fminf chain).
+template <int K, bool VEC, int SD, bool ZERO, int PF, int WPB, int NR>
 __global__ void __launch_bounds__(32 * WPB)
 sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, float *__restrict__ out,
 		int H, int W, int D, int pad, SgmParams prm)
@@ -149,15 +152,15 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 	constexpr int VSZ = 32 * K;                    // floats per cost vector slot (padded to 32*K)
 	constexpr int NV = ZERO ? 1 : 2;               // ring holds `in` (and `out` unless ZERO)
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const int line = blockIdx.x * WPB + wib;
+	const int line0 = (blockIdx.x * WPB + wib) * NR;
 	const int nlines = SD < 2 ? H : W;
 	const int nsteps = SD < 2 ? W : H;
-	if (line >= nlines) return;                    // whole warp
+	if (line0 >= nlines) return;                   // whole warp
 
 	constexpr int dx = SD == 0 ? 1 : (SD == 1 ? -1 : 0);
 	constexpr int dy = SD == 2 ? 1 : (SD == 3 ? -1 : 0);
 	const int dbase = lane * K;
-	float *ring = sgm_smem + (size_t)wib * PF * NV * VSZ + dbase;   // this lane's K floats of slot 0
+	float *ring = sgm_smem + (size_t)wib * NR * PF * NV * VSZ + dbase;   // this lane's K floats of slot 0
 
 	// adcensus.cu:595-605 and :609/:612, same expressions
 	const float P1f = prm.pi1, P2f = prm.pi2;
@@ -174,106 +177,124 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 	const uint8_t *t2 = tab + (SD < 2 ? 2 : 3) * plane + pad;
 	constexpr int tshift_x = dx < 0 ? 1 : 0;
 	constexpr int tshift_y = dy < 0 ? 1 : 0;
-
-	int x = SD == 0 ? 0 : (SD == 1 ? W - 1 : line);
-	int y = SD == 2 ? 0 : (SD == 3 ? H - 1 : line);
-	const long pix_step = (long)(dy * W + dx) * D;
-	long base = ((long)y * W + x) * D + dbase;
 	const int ddir = prm.direction;
+	const long pix_step = (long)(dy * W + dx) * D;
+
+	bool live[NR];
+	int x[NR], y[NR];
+	long base[NR];
+	float *rg[NR];
+#pragma unroll
+	for (int r = 0; r < NR; r++) {
+		const int line = line0 + r;
+		live[r] = line < nlines;                   // warp-uniform
+		const int ln = live[r] ? line : line0;
+		x[r] = SD == 0 ? 0 : (SD == 1 ? W - 1 : ln);
+		y[r] = SD == 2 ? 0 : (SD == 3 ? H - 1 : ln);
+		base[r] = ((long)y[r] * W + x[r]) * D + dbase;
+		rg[r] = ring + r * PF * NV * VSZ;
+	}
 
 	// NaN in the padding slots (never overwritten), then fill the ring
 #pragma unroll
-	for (int s = 0; s < PF * NV; s++)
+	for (int s = 0; s < NR * PF * NV; s++)
 #pragma unroll
 		for (int k = 0; k < K; k++) ring[s * VSZ + k] = adc_nan();
 #pragma unroll
 	for (int u = 0; u < PF; u++) {
-		if (u < nsteps) {
-			issue_vec<K, VEC>(ring + (u * NV) * VSZ, in + base + u * pix_step, dbase, D);
-			if (!ZERO) issue_vec<K, VEC>(ring + (u * NV + 1) * VSZ, out + base + u * pix_step, dbase, D);
-		}
+#pragma unroll
+		for (int r = 0; r < NR; r++)
+			if (live[r] && u < nsteps) {
+				issue_vec<K, VEC>(rg[r] + (u * NV) * VSZ, in + base[r] + u * pix_step, dbase, D);
+				if (!ZERO) issue_vec<K, VEC>(rg[r] + (u * NV + 1) * VSZ, out + base[r] + u * pix_step, dbase, D);
+			}
 		asm volatile("cp.async.commit_group;");
 	}
 
 	// penalty classes are fetched one step ahead (the row of the table changes every step of a
 	// vertical scan, so these loads miss L1; fetched just in time they were the top stall)
-	uint8_t c1n = 0, c2n[K];
-	auto fetch_classes = [&](int xs, int ys) {
+	uint8_t c1n[NR], c2n[NR][K];
+	auto fetch_classes = [&](int r, int xs, int ys) {
 		const int ty = min(max(ys + tshift_y, 0), H - 1);   // row / column of the stored difference
 		const uint8_t *q = t2 + (long)ty * Wp + xs + tshift_x + dbase * ddir;  // D2 classes (:588-594)
-		c1n = __ldg(t1 + (long)ty * Wp + xs + tshift_x);                        // D1 class (:587)
+		c1n[r] = __ldg(t1 + (long)ty * Wp + xs + tshift_x);                     // D1 class (:587)
 #pragma unroll
-		for (int k = 0; k < K; k++) c2n[k] = __ldg(q + k * ddir);
+		for (int k = 0; k < K; k++) c2n[r][k] = __ldg(q + k * ddir);
 	};
-	fetch_classes(x + dx, y + dy);                       // for step 1
+#pragma unroll
+	for (int r = 0; r < NR; r++) fetch_classes(r, x[r] + dx, y[r] + dy);      // for step 1
 
-	float prev[K];
+	float prev[NR][K];
 	for (int s0 = 0; s0 < nsteps; s0 += PF) {
 #pragma unroll
 		for (int u = 0; u < PF; u++) {
 			const int s = s0 + u;
 			if (s >= nsteps) break;
 			asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1));
-			float cin[K], cout[K];
-			read_slot<K>(cin, ring + (u * NV) * VSZ);
-			if (!ZERO) read_slot<K>(cout, ring + (u * NV + 1) * VSZ);
+#pragma unroll
+			for (int r = 0; r < NR; r++) {
+				if (!live[r]) continue;
+				float cin[K], cout[K];
+				read_slot<K>(cin, rg[r] + (u * NV) * VSZ);
+				if (!ZERO) read_slot<K>(cout, rg[r] + (u * NV + 1) * VSZ);
 
-			float val[K];
-			if (s == 0) {                                   // adcensus.cu:567-572
+				float val[K];
+				if (s == 0) {                                   // adcensus.cu:567-572
 #pragma unroll
-				for (int k = 0; k < K; k++) val[k] = cin[k];
-			} else {
-				float mt[K];
+					for (int k = 0; k < K; k++) val[k] = cin[k];
+				} else {
+					float mt[K];
 #pragma unroll
-				for (int k = 0; k < K; k++) mt[k] = prev[k];
+					for (int k = 0; k < K; k++) mt[k] = prev[r][k];
 #pragma unroll
-				for (int w = K / 2; w > 0; w >>= 1)
+					for (int w = K / 2; w > 0; w >>= 1)
 #pragma unroll
-					for (int k = 0; k < w; k++) mt[k] = fminf(mt[k], mt[k + w]);
-				const float m = warp_min_f32(mt[0]);            // :579-584
-				float left = __shfl_up_sync(0xffffffffu, prev[K - 1], 1);
-				float right = __shfl_down_sync(0xffffffffu, prev[0], 1);
-				if (lane == 0) left = adc_nan();                // d - 1 < 0 (:608)
-				if (lane == 31) right = adc_nan();
+						for (int k = 0; k < w; k++) mt[k] = fminf(mt[k], mt[k + w]);
+					const float m = warp_min_f32(mt[0]);            // :579-584
+					float left = __shfl_up_sync(0xffffffffu, prev[r][K - 1], 1);
+					float right = __shfl_down_sync(0xffffffffu, prev[r][0], 1);
+					if (lane == 0) left = adc_nan();                // d - 1 < 0 (:608)
+					if (lane == 31) right = adc_nan();
 
-				const uint8_t c1 = c1n;
-				uint8_t c2[K];
+					const uint8_t c1 = c1n[r];
+					uint8_t c2[K];
 #pragma unroll
-				for (int k = 0; k < K; k++) c2[k] = c2n[k];
-				fetch_classes(x + dx, y + dy);                  // for step s + 1
-				// penalties when the D2 class equals the D1 class (both < tau or both > tau), else middle
-				const bool c1lt = c1 == 0;
-				const float P1e = c1 == 1 ? P1m : (c1lt ? P1f : P1s);
-				const float P2e = c1 == 1 ? P2m : (c1lt ? P2f : P2s);
-				const float P1ae = c1 == 1 ? P1m_a : (c1lt ? P1f_a : P1s_a);
+					for (int k = 0; k < K; k++) c2[k] = c2n[r][k];
+					fetch_classes(r, x[r] + dx, y[r] + dy);         // for step s + 1
+					// penalties when the D2 class equals the D1 class (both < tau or both > tau), else middle
+					const bool c1lt = c1 == 0;
+					const float P1e = c1 == 1 ? P1m : (c1lt ? P1f : P1s);
+					const float P2e = c1 == 1 ? P2m : (c1lt ? P2f : P2s);
+					const float P1ae = c1 == 1 ? P1m_a : (c1lt ? P1f_a : P1s_a);
+#pragma unroll
+					for (int k = 0; k < K; k++) {
+						const bool eq = c2[k] == c1;
+						const float P1 = eq ? P1e : P1m, P2 = eq ? P2e : P2m, P1a = eq ? P1ae : P1m_a;
+						const float pm = k > 0 ? prev[r][k - 1] : left;
+						const float pp = k < K - 1 ? prev[r][k + 1] : right;
+						float cost = fminf(prev[r][k], m + P2);                            // :607
+						cost = fminf(cost, pm + (SD == 2 ? P1a : P1));                     // :609
+						cost = fminf(cost, pp + (SD == 3 ? P1a : P1));                     // :612
+						val[k] = cin[k] + cost - m;                                        // :615
+					}
+				}
+				float o[K];
 #pragma unroll
 				for (int k = 0; k < K; k++) {
-					const bool eq = c2[k] == c1;
-					const float P1 = eq ? P1e : P1m, P2 = eq ? P2e : P2m, P1a = eq ? P1ae : P1m_a;
-					const float pm = k > 0 ? prev[k - 1] : left;
-					const float pp = k < K - 1 ? prev[k + 1] : right;
-					float cost = fminf(prev[k], m + P2);                               // :607
-					cost = fminf(cost, pm + (SD == 2 ? P1a : P1));                     // :609
-					cost = fminf(cost, pp + (SD == 3 ? P1a : P1));                     // :612
-					val[k] = cin[k] + cost - m;                                        // :615
+					o[k] = (ZERO ? 0.0f : cout[k]) + val[k];                               // :569 / :616
+					prev[r][k] = val[k];                                                   // :570 / :617
 				}
-			}
-			float o[K];
-#pragma unroll
-			for (int k = 0; k < K; k++) {
-				o[k] = (ZERO ? 0.0f : cout[k]) + val[k];                               // :569 / :616
-				prev[k] = val[k];                                                      // :570 / :617
-			}
-			store_vec<K, VEC>(o, out + base, dbase, D);
-			// refill this ring slot with step s + PF (its values are in registers by now)
-			if (s + PF < nsteps) {
-				issue_vec<K, VEC>(ring + (u * NV) * VSZ, in + base + PF * pix_step, dbase, D);
-				if (!ZERO) issue_vec<K, VEC>(ring + (u * NV + 1) * VSZ, out + base + PF * pix_step, dbase, D);
+				store_vec<K, VEC>(o, out + base[r], dbase, D);
+				// refill this ring slot with step s + PF (its values are in registers by now)
+				if (s + PF < nsteps) {
+					issue_vec<K, VEC>(rg[r] + (u * NV) * VSZ, in + base[r] + PF * pix_step, dbase, D);
+					if (!ZERO) issue_vec<K, VEC>(rg[r] + (u * NV + 1) * VSZ, out + base[r] + PF * pix_step, dbase, D);
+				}
+				base[r] += pix_step;
+				x[r] += dx;
+				y[r] += dy;
 			}
 			asm volatile("cp.async.commit_group;");
-			base += pix_step;
-			x += dx;
-			y += dy;
 		}
 	}
 	asm volatile("cp.async.wait_group 0;");
@@ -286,9 +307,10 @@ int launch_pass(const uint8_t *tab, const float *in, float *out, int H, int W, i
 	constexpr int PF = K >= 16 ? 6 : 8;
 	// horizontal scans have few, long lines: one warp per CTA spreads them over all SMs
 	constexpr int WPB = SD < 2 ? 1 : 4;
+	constexpr int NR = 1;  // NR = 2 measured 2x slower: the two recurrences are not interleaved by ptxas
 	constexpr int NV = ZERO ? 1 : 2;
-	constexpr int SMEM = WPB * PF * NV * 32 * K * 4;
-	auto kern = sgm_pass_kernel<K, VEC, SD, ZERO, PF, WPB>;
+	constexpr int SMEM = WPB * NR * PF * NV * 32 * K * 4;
+	auto kern = sgm_pass_kernel<K, VEC, SD, ZERO, PF, WPB, NR>;
 	if (SMEM > 48 * 1024) {
 		static bool done[64] = {false};
 		int dev = 0;
@@ -299,7 +321,7 @@ int launch_pass(const uint8_t *tab, const float *in, float *out, int H, int W, i
 		}
 	}
 	const int nlines = SD < 2 ? H : W;
-	kern<<<adc_div_up(nlines, WPB), 32 * WPB, SMEM, s>>>(tab, in, out, H, W, D, pad, prm);
+	kern<<<adc_div_up(nlines, WPB * NR), 32 * WPB, SMEM, s>>>(tab, in, out, H, W, D, pad, prm);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }

@@ -188,3 +188,22 @@ class StereoPipeline:
         rc = adcensus.lib().mccnn_pipeline_run_host(self._h, p(featL), p(featR), p(imgL), p(imgR), p(disp))
         adcensus._check(rc, n)
         return disp
+
+    def run_host_batch(self, pairs, disps=None):
+        """``pairs``: list of (featL, featR, imgL, imgR) host float32 tensors (pinned for overlap).
+        H2D of pair i+1 and D2H of pair i-1 overlap the kernels of pair i.  Returns the list of
+        host disparity maps (synchronous)."""
+        n = "mccnn_pipeline_run_host_batch"
+        k = len(pairs)
+        for pr in pairs:
+            for t in pr:
+                if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise adcensus.AdcensusError("%s: contiguous host float tensors expected" % n)
+        if disps is None:
+            disps = [torch.empty((self.H, self.W), dtype=torch.float32).pin_memory() for _ in range(k)]
+        arr = lambda ts: (ctypes.c_void_p * k)(*[t.data_ptr() for t in ts])
+        rc = adcensus.lib().mccnn_pipeline_run_host_batch(
+            self._h, k, arr([p[0] for p in pairs]), arr([p[1] for p in pairs]), arr([p[2] for p in pairs]),
+            arr([p[3] for p in pairs]), arr(disps))
+        adcensus._check(rc, n)
+        return disps

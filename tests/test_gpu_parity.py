@@ -254,6 +254,13 @@ def test_pipeline_vs_oracle(oracle, H, W, C, D, preset, over):
     h = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     disp_h = sp.run_host(h(p["featL"]), h(p["featR"]), h(p["imgL"]), h(p["imgR"]))
     same(disp_h, want, "disp.bin (host call)")
+    # (d) batched host call: copies of neighbouring pairs overlap the kernels; results stay per pair
+    p2 = synth.make_pair(H, W, C, D, seed=H * 3 + D + 1)
+    want2 = oracle.stereo_predict(p2["featL"], p2["featR"], p2["imgL"], p2["imgR"], D, oracle.Params(**opt.as_dict()))
+    hp = lambda q: (h(q["featL"]), h(q["featR"]), h(q["imgL"]), h(q["imgR"]))
+    outs = sp.run_host_batch([hp(p), hp(p2), hp(p), hp(p2), hp(p)])
+    for i, o in enumerate(outs):
+        same(o, want if i % 2 == 0 else want2, "disp.bin (host batch, pair %d)" % i)
     sp.close()
 
 
@@ -302,6 +309,46 @@ def test_against_live_reference():
         same(volR, wR, "right.bin vs reference")
         same(disp, want, "disp.bin vs reference")
         sp.close()
+
+
+FULL_SIZE = [
+    # BASELINE.json config 2 (KITTI fast, d=70) and config 3 (KITTI accurate, d=228, CBCA x4 + SGM)
+    (370, 1226, 64, 70, ("kitti", "fast"), {}),
+    (370, 1226, 64, 228, ("kitti", "accurate_cbca4"), {}),
+]
+
+
+@pytest.mark.parametrize("H,W,C,D,preset,over", FULL_SIZE)
+def test_full_size_against_live_reference(H, W, C, D, preset, over):
+    """BASELINE.json's full sizes: the fused pipeline against the reference's own kernels run on the
+    same box in main.lua's order -- left.bin, right.bin and disp.bin bit for bit."""
+    from oracle import refdriver
+
+    if not os.path.exists(refdriver.REF_LIB):
+        pytest.skip("oracle/_ref/libadcensus_ref.so not present")
+    shim = refdriver.ShimLibrary(refdriver.REF_LIB)
+    opt = pipeline.make_params(*preset, **over)
+    p = synth.make_pair(H, W, C, D, seed=2)
+    x_batch = cu(np.stack([p["imgL"], p["imgR"]])[:, None])
+    feats = cu(np.stack([p["featL"], p["featR"]]))
+    want, wL, wR = refdriver.stereo_predict(shim, x_batch, feats, opt, D, want_vols=True)
+    sp = pipeline.StereoPipeline(C, D, H, W, opt)
+    volL = torch.empty((D, H, W), device=dev())
+    volR = torch.empty((D, H, W), device=dev())
+    disp = sp.run(feats[0], feats[1], x_batch[0, 0], x_batch[1, 0], volL=volL, volR=volR)
+    torch.cuda.synchronize()
+    # compare on the device (0.4 GB volumes): equal values or both NaN
+    for got, ref, what in ((volL, wL[0], "left.bin"), (volR, wR[0], "right.bin"), (disp, want[0, 0], "disp.bin")):
+        bad = ~((got == ref) | (torch.isnan(got) & torch.isnan(ref)))
+        assert int(bad.sum()) == 0, "%s: %d elements differ from the reference at full size" % (what, int(bad.sum()))
+    # size-independent properties of the domain at full size
+    d = disp.cpu().numpy()
+    assert not np.isnan(d).any() and d.min() >= 0 and d.max() <= D - 1 + 1e-3          # main.lua:1224
+    assert (np.abs(d - p["gt"]) < 1.0).mean() > 0.6                                    # recovers the synthetic GT
+    vl = volL[:, H // 2, :].cpu().numpy()
+    for dd in range(0, D, 37):                                                         # NaN triangle intact
+        assert np.isnan(vl[dd, :dd]).all() and not np.isnan(vl[dd, dd:]).any()
+    sp.close()
 
 
 def test_lua_face_through_the_reference_driver(oracle):
