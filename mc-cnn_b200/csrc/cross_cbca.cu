@@ -21,6 +21,8 @@
 // Roofline: read V + write V (V = 4*D*H*W bytes) per iteration; this exact-order
 // version is bound by shared-memory/FADD issue (one dependent FADD per tap), not
 // by HBM -- see DESIGN.md.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -72,72 +74,53 @@ __global__ void pack_arms_kernel(const float *__restrict__ xc, uint32_t *__restr
 	if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxlen, m);
 }
 
-// ------------------------------------------------------------------ cbca, fixed-window register stencil
+// ------------------------------------------------------------------ cbca, fixed-window column strips
 // (arms up to 5 pixels: every KITTI preset, main.lua:86-113,207-262)
 //
-// A thread owns 4 consecutive x times 2 consecutive y outputs of one disparity plane and walks the
-// 2R+2 tile rows that cover both supports once: per row it loads the 4+2R window columns
-// (LDS.128) and the 4 combined arm words into registers and then issues, for every output and
-// every window slot, one compare (slot inside the run AND row inside the vertical arm) and one
-// predicated FADD.  No data-dependent loop, no divergence; the order of additions per output is
-// still rows ascending, columns ascending, so results stay bit-identical to adcensus.cu:361-370.
-constexpr int CW_TX = 128, CW_TY = 16, CW_DCH = 16, CW_NT = 256;
+// A thread owns ONE column and NVT = 16 consecutive output rows of one disparity plane and walks
+// the NVT + 2R tile rows covering all their supports once.  Per tile row it loads the 2R+1 window
+// columns and the row's combined arm word, and masks the window ONCE: slots outside the row's
+// horizontal run become +0.0f (one compare + one select per slot, shared by every output that
+// uses this row).  Each of the up to 2R+1 outputs whose vertical arm may contain the row then
+// needs one compare (row inside its vertical arm, adcensus.cu:361) and 2R+1 adds predicated on
+// that single predicate.  Adding +0.0f for a masked slot is exact: the accumulator starts at
+// +0.0f and a sum can only be -0.0f if both operands are, so it never is, and x + (+0.0f) == x
+// for every other x (NaN and Inf included).  The order of the real additions per output is still
+// rows ascending, columns ascending => bit-identical to adcensus.cu:361-370, at ~1.3 issued
+// instructions per window slot instead of 2 (the kernel is issue-bound, not HBM-bound).
+// No data-dependent loop, no divergence; stores are 32 consecutive columns per warp instruction.
+constexpr int CW_TX = 128, CW_NVT = 16, CW_TY = 2 * CW_NVT, CW_DCH_MAX = 24, CW_NT = 256;
 
 template <int R>
 struct CWCfg {
 	static constexpr int TH = CW_TY + 2 * R;
-	static constexpr int NV = (4 + 2 * R + 3) / 4;              // float4 loads per window row
-	static constexpr int TWP = ((CW_TX + 2 * R + 3) / 4) * 4 + ((NV * 4 > 4 + 2 * R) ? 4 : 0);
-	static constexpr int A1W = CW_TX + CW_DCH;
+	static constexpr int TWP = CW_TX + 2 * R + 1;               // odd pitch: conflict-free column walks
+	static constexpr int A1W = CW_TX + CW_DCH_MAX;             // right-image arm window for up to CW_DCH_MAX disparities
 	static constexpr int SMEM = (TH * CW_TX + TH * A1W + TH * CW_TX + TH * TWP) * 4;
 };
 
-// One output, one support row: q = row inside the vertical arm; then for every window slot one
-// compare (slot inside the horizontal run, ANDed with q) and one predicated add.f32, in column
-// order.  Inline PTX because nvcc otherwise lowers `if (p) acc += w` to FADD + FSEL.
+// One output, one support row.  qf = 1.0f if the row lies inside the output's vertical arm
+// (adcensus.cu:361), else 0.0f.  fmaf(w, 1.0f, acc) is exactly acc + w (one rounding of the same
+// real number) and fmaf(w, 0.0f, acc) is acc + (+-0.0f) = acc for the never-negative-zero acc, so
+// the 2R+1 masked window values and the row's tap count are accumulated without any predicate
+// (nine live outputs per row would otherwise spill the 7 predicate registers).  Requires finite
+// window values inside a row's run, which holds for every volume whose NaNs are confined to the
+// invalid triangle (the run never reaches it).
 template <int R>
-__device__ __forceinline__ void row_taps(float &acc, int &cnt, const float *w, int L, int Rr, int LR, int va, int vthr);
-
-template <>
-__device__ __forceinline__ void row_taps<4>(float &acc, int &cnt, const float *w, int L, int Rr, int LR, int va, int vthr)
+__device__ __forceinline__ void strip_row(float &acc, float &cnt, const float *wm, float LRf, float qf)
 {
-	asm("{\n\t.reg .pred q, p;\n\t"
-	    "setp.gt.s32 q, %13, %14;\n\t"
-	    "setp.gt.and.s32 p, %11, 4, q;\n\t@p add.f32 %0, %0, %2;\n\t"
-	    "setp.gt.and.s32 p, %11, 3, q;\n\t@p add.f32 %0, %0, %3;\n\t"
-	    "setp.gt.and.s32 p, %11, 2, q;\n\t@p add.f32 %0, %0, %4;\n\t"
-	    "setp.gt.and.s32 p, %11, 1, q;\n\t@p add.f32 %0, %0, %5;\n\t"
-	    "@q add.f32 %0, %0, %6;\n\t"
-	    "setp.gt.and.s32 p, %12, 1, q;\n\t@p add.f32 %0, %0, %7;\n\t"
-	    "setp.gt.and.s32 p, %12, 2, q;\n\t@p add.f32 %0, %0, %8;\n\t"
-	    "setp.gt.and.s32 p, %12, 3, q;\n\t@p add.f32 %0, %0, %9;\n\t"
-	    "setp.gt.and.s32 p, %12, 4, q;\n\t@p add.f32 %0, %0, %10;\n\t"
-	    "@q add.s32 %1, %1, %15;\n\t}"
-	    : "+f"(acc), "+r"(cnt)
-	    : "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]), "f"(w[4]), "f"(w[5]), "f"(w[6]), "f"(w[7]), "f"(w[8]),
-	      "r"(L), "r"(Rr), "r"(va), "r"(vthr), "r"(LR));
-}
-
-template <>
-__device__ __forceinline__ void row_taps<1>(float &acc, int &cnt, const float *w, int L, int Rr, int LR, int va, int vthr)
-{
-	asm("{\n\t.reg .pred q, p;\n\t"
-	    "setp.gt.s32 q, %7, %8;\n\t"
-	    "setp.gt.and.s32 p, %5, 1, q;\n\t@p add.f32 %0, %0, %2;\n\t"
-	    "@q add.f32 %0, %0, %3;\n\t"
-	    "setp.gt.and.s32 p, %6, 1, q;\n\t@p add.f32 %0, %0, %4;\n\t"
-	    "@q add.s32 %1, %1, %9;\n\t}"
-	    : "+f"(acc), "+r"(cnt)
-	    : "f"(w[0]), "f"(w[1]), "f"(w[2]), "r"(L), "r"(Rr), "r"(va), "r"(vthr), "r"(LR));
+#pragma unroll
+	for (int k = 0; k <= 2 * R; k++) acc = fmaf(wm[k], qf, acc);                 // :364-367
+	cnt = fmaf(LRf, qf, cnt);                                                     // :368
 }
 
 template <int R>
-__global__ void __launch_bounds__(CW_NT, 4)
+__global__ void __launch_bounds__(CW_NT, 2)
 cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
-		const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction)
+		const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction, int dch)
 {
 	using Cfg = CWCfg<R>;
-	constexpr int TH = Cfg::TH, TWP = Cfg::TWP, A1W = Cfg::A1W, NV = Cfg::NV;
+	constexpr int TH = Cfg::TH, TWP = Cfg::TWP, A1W = Cfg::A1W;
 	extern __shared__ __align__(16) uint32_t cw_smem[];
 	uint32_t *sa0 = cw_smem;                       // [TH][CW_TX]  left-image arms of the tile
 	uint32_t *sa1 = sa0 + TH * CW_TX;              // [TH][A1W]    right-image arms, shifted window
@@ -145,13 +128,13 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 	float *sv = reinterpret_cast<float *>(scomb + TH * CW_TX);  // [TH][TWP] volume plane tile + halo
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int x0 = blockIdx.x * CW_TX, y0 = blockIdx.y * CW_TY, d0 = blockIdx.z * CW_DCH;
-	const int dn = min(CW_DCH, D - d0);
-	const int a1x0 = direction > 0 ? x0 + d0 : x0 - (d0 + CW_DCH - 1);
+	const int x0 = blockIdx.x * CW_TX, y0 = blockIdx.y * CW_TY, d0 = blockIdx.z * dch;   // dch <= CW_DCH_MAX disparities per CTA
+	const int dn = min(dch, D - d0);
+	const int a1x0 = direction > 0 ? x0 + d0 : x0 - (d0 + dch - 1);
 	const long HW = (long)H * W;
 
-	const int cx = 4 * lane;                       // first of this thread's 4 tile columns
-	const int ry = 2 * warp;                       // first of this thread's 2 output rows (tile-relative)
+	const int cx = 32 * (warp & 3) + lane;         // this thread's tile column
+	const int ry = CW_NVT * (warp >> 2);           // first of its NVT output rows (tile-relative)
 	constexpr int NW = CW_NT / 32;
 
 	// packed arms: one warp per tile row, lanes along x (no index division anywhere)
@@ -177,14 +160,11 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 		// whole tile inside the invalid triangle (x + d*direction outside the image for every
 		// column): plain copy, adcensus.cu:353-354 (CTA-uniform, so no barrier is skipped unevenly)
 		if (direction < 0 ? (x0 + CW_TX - 1 - d < 0) : (x0 + d >= W)) {
+			const int x = x0 + cx;
 #pragma unroll
-			for (int oy = 0; oy < 2; oy++) {
+			for (int oy = 0; oy < CW_NVT; oy++) {
 				const int y = y0 + ry + oy;
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					const int x = x0 + cx + j;
-					if (y < H && x < W) out[(long)d * HW + (long)y * W + x] = __ldg(plane + (long)y * W + x);
-				}
+				if (y < H && x < W) out[(long)d * HW + (long)y * W + x] = __ldg(plane + (long)y * W + x);
 			}
 			continue;
 		}
@@ -207,80 +187,60 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 			}
 		}
 		asm volatile("cp.async.commit_group;");
-		// combined arms of this disparity: this thread's 4 columns of every NW-th row
+		// combined arms of this disparity (byte-wise min of the left arms at x and the right arms at x + d*dir)
 		for (int r = warp; r < TH; r += NW) {
-			uint4 a = *reinterpret_cast<const uint4 *>(sa0 + r * CW_TX + cx);
-			const uint32_t *b = sa1 + r * A1W + cx + off;
-			uint4 c;
-			c.x = __vminu4(a.x, b[0]);
-			c.y = __vminu4(a.y, b[1]);
-			c.z = __vminu4(a.z, b[2]);
-			c.w = __vminu4(a.w, b[3]);
-			*reinterpret_cast<uint4 *>(scomb + r * CW_TX + cx) = c;
+#pragma unroll
+			for (int m = 0; m < CW_TX / 32; m++) {
+				const int c = lane + 32 * m;
+				scomb[r * CW_TX + c] = __vminu4(sa0[r * CW_TX + c], sa1[r * A1W + c + off]);
+			}
 		}
 		asm volatile("cp.async.wait_group 0;");
 		__syncthreads();
 
-		int U[2][4], Dn[2][4];
+		int U[CW_NVT], Dn[CW_NVT];
+		float acc[CW_NVT], cnt[CW_NVT];
 #pragma unroll
-		for (int oy = 0; oy < 2; oy++) {
-			uint4 cc = *reinterpret_cast<const uint4 *>(scomb + (ry + oy + R) * CW_TX + cx);
-			uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
-#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				U[oy][j] = (c4[j] >> 16) & 255;
-				Dn[oy][j] = c4[j] >> 24;
-			}
+		for (int oy = 0; oy < CW_NVT; oy++) {
+			const uint32_t c = scomb[(ry + oy + R) * CW_TX + cx];
+			U[oy] = (c >> 16) & 255;
+			Dn[oy] = c >> 24;
+			acc[oy] = 0.0f;
+			cnt[oy] = 0.0f;
 		}
-		float acc[2][4];
-		int cnt[2][4];
-#pragma unroll
-		for (int oy = 0; oy < 2; oy++)
-#pragma unroll
-			for (int j = 0; j < 4; j++) { acc[oy][j] = 0.0f; cnt[oy][j] = 0; }
 
 #pragma unroll
-		for (int ri = 0; ri < 2 * R + 2; ri++) {
-			float w[NV * 4];
-			const float *wrow = sv + (ry + ri) * TWP + cx;
+		for (int ri = 0; ri < CW_NVT + 2 * R; ri++) {
+			const float *wrow = sv + (ry + ri) * TWP + cx;     // window column k of this thread: image column x - R + k
+			const uint32_t c = scomb[(ry + ri) * CW_TX + cx];
+			const int L = c & 255, Rr = (c >> 8) & 255;
+			const float LRf = (float)(L + Rr - 1);             // taps of this row's run (:364-369), exact in fp32
+			float wm[2 * R + 1];
 #pragma unroll
-			for (int v = 0; v < NV; v++)
-				*reinterpret_cast<float4 *>(&w[4 * v]) = *reinterpret_cast<const float4 *>(wrow + 4 * v);
-			uint4 cc = *reinterpret_cast<const uint4 *>(scomb + (ry + ri) * CW_TX + cx);
-			uint32_t c4[4] = {cc.x, cc.y, cc.z, cc.w};
-			int L[4], Rr[4], LR[4];
-#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				L[j] = c4[j] & 255;
-				Rr[j] = (c4[j] >> 8) & 255;
-				LR[j] = L[j] + Rr[j] - 1;              // taps of this row's run (:364-369)
+			for (int k = 0; k <= 2 * R; k++) {
+				const float v = wrow[k];
+				// slot inside the run (x - L, x + Rr) (:362-364); the centre slot is, unless the row has no arms (outside the image)
+				wm[k] = k < R ? (L > R - k ? v : 0.0f) : (k > R ? (Rr > k - R ? v : 0.0f) : (L > 0 ? v : 0.0f));
 			}
 #pragma unroll
-			for (int oy = 0; oy < 2; oy++) {
-				const int delta = ri - oy - R;         // row offset from this output's centre row
+			for (int oy = 0; oy < CW_NVT; oy++) {
+				const int delta = ri - oy - R;                 // row offset from this output's centre row
 				if (delta < -R || delta > R) continue;
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					// row inside this output's vertical arm (:361): centre row iff the output is valid
-					const int va = delta < 0 ? U[oy][j] : Dn[oy][j];
-					const int vthr = delta < 0 ? -delta : delta;  // delta == 0: Dn > 0
-					row_taps<R>(acc[oy][j], cnt[oy][j], &w[j], L[j], Rr[j], LR[j], va, vthr);
-				}
+				// row inside this output's vertical arm (:361); centre row iff the output is valid
+				const int va = delta < 0 ? U[oy] : Dn[oy];
+				const int vthr = delta < 0 ? -delta : delta;
+				strip_row<R>(acc[oy], cnt[oy], wm, LRf, va > vthr ? 1.0f : 0.0f);
 			}
 		}
+		const int x = x0 + cx;
+		const int xs = x + d * direction;
 #pragma unroll
-		for (int oy = 0; oy < 2; oy++) {
+		for (int oy = 0; oy < CW_NVT; oy++) {
 			const int y = y0 + ry + oy;
-			if (y >= H) continue;
-#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				const int x = x0 + cx + j;
-				if (x >= W) continue;
-				const int xs = x + d * direction;
-				float res = (xs < 0 || xs >= W) ? sv[(ry + oy + R) * TWP + cx + j + R]      // :353-354
-								: acc[oy][j] / (float)cnt[oy][j];          // :373
-				out[(long)d * HW + (long)y * W + x] = res;
-			}
+			if (y >= H || x >= W) continue;
+			float res = (xs < 0 || xs >= W) ? sv[(ry + oy + R) * TWP + cx + R]         // :353-354
+							: acc[oy] / cnt[oy];                        // :373
+			out[(long)d * HW + (long)y * W + x] = res;
 		}
 	}
 }
@@ -405,8 +365,15 @@ int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *
 		ADC_CUDA(cudaFuncSetAttribute(cbca_win_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
 		attr_done[dev & 63] = true;
 	}
-	dim3 grid(adc_div_up(W, CW_TX), adc_div_up(H, CW_TY), adc_div_up(D, CW_DCH));
-	cbca_win_kernel<R><<<grid, CW_NT, Cfg::SMEM, s>>>(a0, a1, vol, out, D, H, W, direction);
+	// disparities per CTA.  Measured at 370x1226x228: 4..12 -> 1.01-1.04 ms, 16 -> 1.01 ms, 19 (whole
+	// waves) -> 1.08 ms: the kernel is issue-bound and balances dynamically, so the chunk size hardly
+	// matters; 10 keeps the per-chunk re-staging of the packed arms (L2 traffic only) small.
+	const char *env = getenv("ADCENSUS_CBCA_DCH");   // tuning knob, not part of the ABI
+	int dch = env ? atoi(env) : 10;
+	if (dch < 1) dch = 1;
+	if (dch > CW_DCH_MAX) dch = CW_DCH_MAX;
+	dim3 grid(adc_div_up(W, CW_TX), adc_div_up(H, CW_TY), adc_div_up(D, dch));
+	cbca_win_kernel<R><<<grid, CW_NT, Cfg::SMEM, s>>>(a0, a1, vol, out, D, H, W, direction, dch);
 	return 0;
 }
 
