@@ -86,6 +86,16 @@ int adcensus_sgm2(const float *x0, const float *x1, const float *input, float *o
 		  int H, int W, int D, float pi1, float pi2, float tau_so, float alpha1,
 		  float sgm_q1, float sgm_q2, int direction, adcensus_stream_t stream);
 
+/* Band-wise sgm2 for the row-band / column-band multi-GPU split: x0, x1 are the FULL Ht x Wt images,
+ * input/output this GPU's band volume (H,W,D) at image offset (yoff, xoff); pass_mask selects scan
+ * directions (bit 0 right, 1 left, 2 down, 3 up; run in that order).  A band must hold whole scanlines
+ * of every selected pass (row bands for bits 0-1, column bands for bits 2-3).  zero_out != 0: `output`
+ * is known to be zero on entry. */
+int mccnn_sgm2_band(const float *x0, const float *x1, const float *input, float *output,
+		    int H, int W, int D, int Ht, int Wt, int yoff, int xoff,
+		    float pi1, float pi2, float tau_so, float alpha1, float sgm_q1, float sgm_q2,
+		    int direction, int pass_mask, int zero_out, adcensus_stream_t stream);
+
 /* adcensus.outlier_detection(d0, d1, outlier, disp_max)  adcensus.cu:878-918 */
 int adcensus_outlier_detection(const float *d0, const float *d1, float *outlier,
 			       int H, int W, int disp_max, adcensus_stream_t stream);

@@ -37,6 +37,10 @@ namespace {
 struct SgmParams {
 	float pi1, pi2, tau_so, alpha1, q1, q2;
 	int direction;
+	// band support: the volume (H,W,D) handed to a pass may be a row band or a column band of the
+	// image; its pixel (y, x) is image pixel (yoff + y, xoff + x) of the Ht x Wt image the class
+	// tables were built from.  Bands never cut a scanline of the pass they are used for.
+	int Ht, Wt, yoff, xoff;
 };
 
 // ---------------------------------------------------------------- penalty class tables
@@ -171,10 +175,10 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 	// class tables: D1 from plane (SD<2 ? 0 : 1), D2 from plane (SD<2 ? 2 : 3).  The stored
 	// difference at (y, j) pairs pixel j with its left / upper neighbour, so scans that look
 	// right / down (dx = -1, dy = -1) read the entry one further.
-	const int Wp = W + 2 * pad;
-	const long plane = (long)H * Wp;
-	const uint8_t *t1 = tab + (SD < 2 ? 0 : 1) * plane + pad;
-	const uint8_t *t2 = tab + (SD < 2 ? 2 : 3) * plane + pad;
+	const int Wp = prm.Wt + 2 * pad;
+	const long plane = (long)prm.Ht * Wp;
+	const uint8_t *t1 = tab + (SD < 2 ? 0 : 1) * plane + pad + prm.xoff;
+	const uint8_t *t2 = tab + (SD < 2 ? 2 : 3) * plane + pad + prm.xoff;
 	constexpr int tshift_x = dx < 0 ? 1 : 0;
 	constexpr int tshift_y = dy < 0 ? 1 : 0;
 	const int ddir = prm.direction;
@@ -215,7 +219,7 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 	// vertical scan, so these loads miss L1; fetched just in time they were the top stall)
 	uint8_t c1n[NR], c2n[NR][K];
 	auto fetch_classes = [&](int r, int xs, int ys) {
-		const int ty = min(max(ys + tshift_y, 0), H - 1);   // row / column of the stored difference
+		const int ty = min(max(ys + prm.yoff + tshift_y, 0), prm.Ht - 1);   // image row of the stored difference
 		const uint8_t *q = t2 + (long)ty * Wp + xs + tshift_x + dbase * ddir;  // D2 classes (:588-594)
 		c1n[r] = __ldg(t1 + (long)ty * Wp + xs + tshift_x);                     // D1 class (:587)
 #pragma unroll
@@ -326,17 +330,20 @@ int launch_pass(const uint8_t *tab, const float *in, float *out, int H, int W, i
 	return 0;
 }
 
+// pass_mask bit i = run scan direction i (0 right, 1 left, 2 down, 3 up), always in that order
 template <int K, bool VEC>
 int launch_all(const uint8_t *tab, const float *in, float *out, int H, int W, int D, int pad,
-	       const SgmParams &prm, bool zero_out, cudaStream_t s)
+	       const SgmParams &prm, bool zero_out, int pass_mask, cudaStream_t s)
 {
-	int rc;
-	rc = zero_out ? launch_pass<K, VEC, 0, true>(tab, in, out, H, W, D, pad, prm, s)
-		      : launch_pass<K, VEC, 0, false>(tab, in, out, H, W, D, pad, prm, s);
+	int rc = 0;
+	if (pass_mask & 1)
+		rc = zero_out ? launch_pass<K, VEC, 0, true>(tab, in, out, H, W, D, pad, prm, s)
+			      : launch_pass<K, VEC, 0, false>(tab, in, out, H, W, D, pad, prm, s);
 	if (rc) return rc;
-	if ((rc = launch_pass<K, VEC, 1, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
-	if ((rc = launch_pass<K, VEC, 2, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
-	return launch_pass<K, VEC, 3, false>(tab, in, out, H, W, D, pad, prm, s);
+	if ((pass_mask & 2) && (rc = launch_pass<K, VEC, 1, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
+	if ((pass_mask & 4) && (rc = launch_pass<K, VEC, 2, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
+	if (pass_mask & 8) rc = launch_pass<K, VEC, 3, false>(tab, in, out, H, W, D, pad, prm, s);
+	return rc;
 }
 
 }  // namespace
@@ -347,26 +354,70 @@ static int sgm_slots(int D) { return D <= 32 ? 32 : (D <= 64 ? 64 : (D <= 128 ? 
 
 size_t adc_sgm_table_bytes(int H, int W, int D) { return 4 * (size_t)H * (W + 2 * (size_t)sgm_slots(D)) + 16; }
 
-// zero_out: `output` is known to be all zeros (main.lua:1014) -> first pass skips reading it.
-// tab: scratch of adc_sgm_table_bytes(H, W, D) bytes.
+int adc_sgm_classes(const float *x0, const float *x1, uint8_t *tab, int Ht, int Wt, int D, float tau_so, cudaStream_t s)
+{
+	const int pad = sgm_slots(D);
+	const long plane = (long)Ht * (Wt + 2 * pad);
+	sgm_class_kernel<<<adc_div_up(plane, 256), 256, 0, s>>>(x0, x1, tab, Ht, Wt, pad, tau_so);
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+// The selected passes over a volume (H,W,D) that is the band [yoff, yoff+H) x [xoff, xoff+W) of the
+// Ht x Wt image whose class tables are in `tab` (adc_sgm_classes).  zero_out: `output` is known
+// to be all zeros (main.lua:1014) -> the first (rightward) pass skips reading it.
+int adc_sgm2_band(const float *in, float *out, const uint8_t *tab, int H, int W, int D, int Ht, int Wt, int yoff, int xoff,
+		  float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
+		  bool zero_out, int pass_mask, cudaStream_t s)
+{
+	SgmParams prm{pi1, pi2, tau_so, alpha1, q1, q2, direction, Ht, Wt, yoff, xoff};
+	const int pad = sgm_slots(D);
+	const bool vec = (D % 4 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0);
+	if (D <= 32) return launch_all<1, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
+	if (D <= 64) return launch_all<2, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
+	if (D <= 128) return vec ? launch_all<4, true>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s)
+				 : launch_all<4, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
+	if (D <= 256) return vec ? launch_all<8, true>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s)
+				 : launch_all<8, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
+	return vec ? launch_all<16, true>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s)
+		   : launch_all<16, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
+}
+
+// whole image, all four directions (what adcensus.sgm2 does).  tab: scratch of adc_sgm_table_bytes(H, W, D) bytes.
 int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, uint8_t *tab, int H, int W, int D,
 	     float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
 	     bool zero_out, cudaStream_t s)
 {
-	SgmParams prm{pi1, pi2, tau_so, alpha1, q1, q2, direction};
-	const int pad = sgm_slots(D);
-	const long plane = (long)H * (W + 2 * pad);
-	sgm_class_kernel<<<adc_div_up(plane, 256), 256, 0, s>>>(x0, x1, tab, H, W, pad, tau_so);
-	ADC_CHECK_LAUNCH();
-	const bool vec = (D % 4 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0);
-	if (D <= 32) return launch_all<1, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
-	if (D <= 64) return launch_all<2, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
-	if (D <= 128) return vec ? launch_all<4, true>(tab, in, out, H, W, D, pad, prm, zero_out, s)
-				 : launch_all<4, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
-	if (D <= 256) return vec ? launch_all<8, true>(tab, in, out, H, W, D, pad, prm, zero_out, s)
-				 : launch_all<8, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
-	return vec ? launch_all<16, true>(tab, in, out, H, W, D, pad, prm, zero_out, s)
-		   : launch_all<16, false>(tab, in, out, H, W, D, pad, prm, zero_out, s);
+	int rc = adc_sgm_classes(x0, x1, tab, H, W, D, tau_so, s);
+	if (rc) return rc;
+	return adc_sgm2_band(in, out, tab, H, W, D, H, W, 0, 0, pi1, pi2, tau_so, alpha1, q1, q2, direction, zero_out, 15, s);
+}
+
+// ---- band-wise entry point for the row-band / column-band multi-GPU split (rowband.py) ----------
+// x0, x1: the FULL Ht x Wt images (replicated on every GPU); input/output: this GPU's band volume
+// (H,W,D) at image offset (yoff, xoff); pass_mask selects scan directions (bit 0 right, 1 left,
+// 2 down, 3 up).  A band must contain whole scanlines of every selected pass: row bands
+// (W == Wt, xoff == 0) for the horizontal passes, column bands (H == Ht, yoff == 0) for the vertical.
+extern "C" int mccnn_sgm2_band(const float *x0, const float *x1, const float *input, float *output,
+			       int H, int W, int D, int Ht, int Wt, int yoff, int xoff,
+			       float pi1, float pi2, float tau_so, float alpha1, float sgm_q1, float sgm_q2,
+			       int direction, int pass_mask, int zero_out, adcensus_stream_t stream)
+{
+	if (!x0 || !x1 || !input || !output || input == output) return ADCENSUS_EINVAL;
+	if (H < 1 || W < 1 || D < 1 || Ht < H || Wt < W || yoff < 0 || xoff < 0 || yoff + H > Ht || xoff + W > Wt) return ADCENSUS_EINVAL;
+	if ((direction != 1 && direction != -1) || (pass_mask & ~15)) return ADCENSUS_EINVAL;
+	if ((pass_mask & 3) && (W != Wt || xoff != 0)) return ADCENSUS_EINVAL;   // horizontal scanlines must be whole
+	if ((pass_mask & 12) && (H != Ht || yoff != 0)) return ADCENSUS_EINVAL;  // vertical scanlines must be whole
+	if (D > ADCENSUS_MAX_DISP) return ADCENSUS_ELIMIT;
+	cudaStream_t s = adc_stream(stream);
+	uint8_t *tab = nullptr;
+	int rc = adc_scratch_alloc((void **)&tab, adc_sgm_table_bytes(Ht, Wt, D), s);
+	if (rc) return rc;
+	rc = adc_sgm_classes(x0, x1, tab, Ht, Wt, D, tau_so, s);
+	if (!rc) rc = adc_sgm2_band(input, output, tab, H, W, D, Ht, Wt, yoff, xoff, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2,
+				    direction, zero_out != 0, pass_mask, s);
+	int rc2 = adc_scratch_free(tab, s);
+	return rc ? rc : rc2;
 }
 
 extern "C" int adcensus_sgm2(const float *x0, const float *x1, const float *input, float *output, float *tmp,

@@ -215,8 +215,11 @@ void orc_cbca(const float *x0c, const float *x1c, const float *vol, float *out, 
 static void sgm2_step(int sgm_direction, int line, int step,
 		      const float *x0, const float *x1, const float *in, float *out, float *tmp,
 		      int H, int W, int D, float pi1, float pi2, float tau_so, float alpha1,
-		      float sgm_q1, float sgm_q2, int direction)
+		      float sgm_q1, float sgm_q2, int direction, int Wt, int yoff, int xoff)
 {
+	/* (H,W,D) may be a band of the Ht x Wt image: volume pixel (y,x) is image pixel (yoff+y, xoff+x);
+	 * a band holds whole scanlines of the passes run on it, so the first-pixel test stays in volume
+	 * coordinates while image look-ups use image coordinates */
 	int x, y, dx, dy;
 	if (sgm_direction == 0) { x = step; y = line; dx = 1; dy = 0; }
 	else if (sgm_direction == 1) { x = W - 1 - step; y = line; dx = -1; dy = 0; }
@@ -239,13 +242,13 @@ static void sgm2_step(int sgm_direction, int line, int step,
 		for (int d = 0; d < i; d++)
 			if (d + i < D && output_min[d + i] < output_min[d]) output_min[d] = output_min[d + i];
 
-	int ind2 = y * W + x;
-	float D1 = fabsf(x0[ind2] - x0[ind2 - dy * W - dx]);                 /* :587 */
+	int ind2 = (y + yoff) * Wt + (x + xoff);
+	float D1 = fabsf(x0[ind2] - x0[ind2 - dy * Wt - dx]);                /* :587 */
 	for (int d = 0; d < D; d++) {
 		float D2;
-		int xx = x + d * direction;
-		if (xx < 0 || xx >= W || xx - dx < 0 || xx - dx >= W) D2 = 10;   /* :590-591 */
-		else D2 = fabsf(x1[ind2 + d * direction] - x1[ind2 + d * direction - dy * W - dx]); /* :593 */
+		int xx = x + xoff + d * direction;
+		if (xx < 0 || xx >= Wt || xx - dx < 0 || xx - dx >= Wt) D2 = 10; /* :590-591 */
+		else D2 = fabsf(x1[ind2 + d * direction] - x1[ind2 + d * direction - dy * Wt - dx]); /* :593 */
 		float P1, P2;
 		if (D1 < tau_so && D2 < tau_so) { P1 = pi1; P2 = pi2; }          /* :596-598 */
 		else if (D1 > tau_so && D2 > tau_so) { P1 = pi1 / (sgm_q1 * sgm_q2); P2 = pi2 / (sgm_q1 * sgm_q2); }
@@ -261,11 +264,15 @@ static void sgm2_step(int sgm_direction, int line, int step,
 	}
 }
 
-void orc_sgm2(const float *x0, const float *x1, const float *in, float *out, float *tmp,
-	      int H, int W, int D, float pi1, float pi2, float tau_so, float alpha1,
-	      float sgm_q1, float sgm_q2, int direction)
+/* the passes selected by pass_mask (bit sd) over a band volume; tmp holds W*D floats, indexed d*W + line
+ * like the reference (adcensus.cu:570): horizontal passes therefore need H <= W (row bands), vertical
+ * passes have line < W by construction */
+void orc_sgm2_band(const float *x0, const float *x1, const float *in, float *out, float *tmp,
+		   int H, int W, int D, int Wt, int yoff, int xoff, float pi1, float pi2, float tau_so, float alpha1,
+		   float sgm_q1, float sgm_q2, int direction, int pass_mask)
 {
 	for (int sd = 0; sd < 4; sd++) {
+		if (!(pass_mask & (1 << sd))) continue;
 		int nlines = sd < 2 ? H : W;
 		int nsteps = sd < 2 ? W : H;
 		/* lines are independent; steps are sequential (one launch each, :639-693) */
@@ -273,8 +280,15 @@ void orc_sgm2(const float *x0, const float *x1, const float *in, float *out, flo
 		for (int line = 0; line < nlines; line++)
 			for (int step = 0; step < nsteps; step++)
 				sgm2_step(sd, line, step, x0, x1, in, out, tmp, H, W, D, pi1, pi2, tau_so,
-					  alpha1, sgm_q1, sgm_q2, direction);
+					  alpha1, sgm_q1, sgm_q2, direction, Wt, yoff, xoff);
 	}
+}
+
+void orc_sgm2(const float *x0, const float *x1, const float *in, float *out, float *tmp,
+	      int H, int W, int D, float pi1, float pi2, float tau_so, float alpha1,
+	      float sgm_q1, float sgm_q2, int direction)
+{
+	orc_sgm2_band(x0, x1, in, out, tmp, H, W, D, W, 0, 0, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction, 15);
 }
 
 /* adcensus.cu:244-262: 1-based argmin over dim 1, strict <, init +inf (NaN skipped) */

@@ -137,6 +137,18 @@ def sgm2(x0, x1, vol_hwd, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction, o
     return out
 
 
+def sgm2_band(x0, x1, vol_hwd, out, Wt, yoff, xoff, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction, pass_mask):
+    """selected passes over a band volume (H,W,D) at image offset (yoff, xoff); x0/x1 are the full images"""
+    x0, x1 = _f(x0), _f(x1)
+    assert vol_hwd.dtype == np.float32 and vol_hwd.flags["C_CONTIGUOUS"] and out.flags["C_CONTIGUOUS"]
+    H, W, D = vol_hwd.shape
+    tmp = np.empty((max(H, W), D), np.float32)
+    cf = ctypes.c_float
+    lib().orc_sgm2_band(_p(x0), _p(x1), _p(vol_hwd), _p(out), _p(tmp), H, W, D, int(Wt), int(yoff), int(xoff),
+                        cf(pi1), cf(pi2), cf(tau_so), cf(alpha1), cf(sgm_q1), cf(sgm_q2), int(direction), int(pass_mask))
+    return out
+
+
 def spatial_argmin(vol):
     vol = _f(vol)
     D, H, W = vol.shape
