@@ -79,15 +79,19 @@ __global__ void pack_arms_kernel(const float *__restrict__ xc, uint32_t *__restr
 //
 // A thread owns ONE column and NVT = 16 consecutive output rows of one disparity plane and walks
 // the NVT + 2R tile rows covering all their supports once.  Per tile row it loads the 2R+1 window
-// columns and the row's combined arm word, and masks the window ONCE: slots outside the row's
-// horizontal run become +0.0f (one compare + one select per slot, shared by every output that
-// uses this row).  Each of the up to 2R+1 outputs whose vertical arm may contain the row then
-// needs one compare (row inside its vertical arm, adcensus.cu:361) and 2R+1 adds predicated on
-// that single predicate.  Adding +0.0f for a masked slot is exact: the accumulator starts at
-// +0.0f and a sum can only be -0.0f if both operands are, so it never is, and x + (+0.0f) == x
-// for every other x (NaN and Inf included).  The order of the real additions per output is still
-// rows ascending, columns ascending => bit-identical to adcensus.cu:361-370, at ~1.3 issued
-// instructions per window slot instead of 2 (the kernel is issue-bound, not HBM-bound).
+// columns and the row's combined horizontal arms (L, R_), and masks the window ONCE: slots outside
+// the run (x - L, x + R_) become +0.0f (one compare + one select per slot, shared by every output
+// that uses this row).  Every output whose vertical arm may contain the row then accumulates
+// acc = fmaf(wm[k], q, acc) in column order with q in {0.0f, 1.0f} (row inside its vertical arm,
+// adcensus.cu:361): no predicates (nine live outputs per row would spill the 7 predicate registers).
+// Exactness: fmaf(w, 1, acc) is acc + w (one rounding of the same real number); fmaf(w, 0, acc)
+// adds +-0.0f to an accumulator that is never -0.0f (it starts at +0.0f and a sum is -0.0f only
+// if both operands are) => acc unchanged.  (Moving the masks to FADD.SAT/FMUL on the FMA pipe and
+// the arm minima to VIMNMX.U16x2 was measured slower: 1.15 ms vs 1.02 ms.)  The order of the real
+// additions per output is rows ascending, columns ascending => bit-identical to adcensus.cu:361-370.
+// The masks are selects, so NaNs of the invalid triangle (never inside a run) are dropped; the
+// accumulation itself needs finite values inside the runs, i.e. a volume that is finite on its
+// valid part (the reference asserts !isnan there, adcensus.cu:366).
 // No data-dependent loop, no divergence; stores are 32 consecutive columns per warp instruction.
 constexpr int CW_TX = 128, CW_NVT = 16, CW_TY = 2 * CW_NVT, CW_DCH_MAX = 24, CW_NT = 256;
 
@@ -96,36 +100,29 @@ struct CWCfg {
 	static constexpr int TH = CW_TY + 2 * R;
 	static constexpr int TWP = CW_TX + 2 * R + 1;               // odd pitch: conflict-free column walks
 	static constexpr int A1W = CW_TX + CW_DCH_MAX;             // right-image arm window for up to CW_DCH_MAX disparities
-	static constexpr int SMEM = (TH * CW_TX + TH * A1W + TH * CW_TX + TH * TWP) * 4;
+	// plane-tile buffers: 2 for the exact kernel (double-buffered), 1 for FAST
+	static constexpr int PW = TWP + 1;                          // prefix row: P[c] = sum of columns < c
+	static constexpr int SMEM = (TH * CW_TX + TH * A1W + TH * CW_TX + 2 * TH * TWP) * 4;
+	static constexpr int SMEM_FAST = (TH * CW_TX + TH * A1W + TH * CW_TX + TH * TWP + TH * PW) * 4;
 };
 
-// One output, one support row.  qf = 1.0f if the row lies inside the output's vertical arm
-// (adcensus.cu:361), else 0.0f.  fmaf(w, 1.0f, acc) is exactly acc + w (one rounding of the same
-// real number) and fmaf(w, 0.0f, acc) is acc + (+-0.0f) = acc for the never-negative-zero acc, so
-// the 2R+1 masked window values and the row's tap count are accumulated without any predicate
-// (nine live outputs per row would otherwise spill the 7 predicate registers).  Requires finite
-// window values inside a row's run, which holds for every volume whose NaNs are confined to the
-// invalid triangle (the run never reaches it).
-template <int R>
-__device__ __forceinline__ void strip_row(float &acc, float &cnt, const float *wm, float LRf, float qf)
-{
-#pragma unroll
-	for (int k = 0; k <= 2 * R; k++) acc = fmaf(wm[k], qf, acc);                 // :364-367
-	cnt = fmaf(LRf, qf, cnt);                                                     // :368
-}
-
-template <int R>
+// FAST (opt-in, NOT bit-exact): each row's run is summed as a difference of per-row prefix sums
+// (built in double, stored in fp32) and added to the output as ONE value, i.e. acc += round(sum of
+// run) instead of acc = (((acc + v1) + v2) + ...).  Same region, same row order, different rounding:
+// volumes agree with the exact mode to ~1e-6 relative (bar: 1e-4).
+template <int R, bool FAST>
 __global__ void __launch_bounds__(CW_NT, 2)
 cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
 		const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction, int dch)
 {
 	using Cfg = CWCfg<R>;
-	constexpr int TH = Cfg::TH, TWP = Cfg::TWP, A1W = Cfg::A1W;
+	constexpr int TH = Cfg::TH, TWP = Cfg::TWP, A1W = Cfg::A1W, PW = Cfg::PW;
 	extern __shared__ __align__(16) uint32_t cw_smem[];
-	uint32_t *sa0 = cw_smem;                       // [TH][CW_TX]  left-image arms of the tile
-	uint32_t *sa1 = sa0 + TH * CW_TX;              // [TH][A1W]    right-image arms, shifted window
-	uint32_t *scomb = sa1 + TH * A1W;              // [TH][CW_TX]  vmin4 of both for the current d
-	float *sv = reinterpret_cast<float *>(scomb + TH * CW_TX);  // [TH][TWP] volume plane tile + halo
+	uint32_t *sa0 = cw_smem;                       // [TH][CW_TX]  left-image packed arms (L | R<<8 | U<<16 | D<<24) of the tile
+	uint32_t *sa1 = sa0 + TH * CW_TX;              // [TH][A1W]    right-image packed arms, shifted window
+	uint32_t *scomb = sa1 + TH * A1W;              // [TH][CW_TX]  byte-wise minimum of both for the current d
+	float *svbuf = reinterpret_cast<float *>(scomb + TH * CW_TX);  // NBUF x [TH][TWP] volume plane tile + halo
+	float *sp = svbuf + (FAST ? 1 : 2) * TH * TWP;                // [TH][PW]  FAST only: row prefix sums
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int x0 = blockIdx.x * CW_TX, y0 = blockIdx.y * CW_TY, d0 = blockIdx.z * dch;   // dch <= CW_DCH_MAX disparities per CTA
@@ -135,6 +132,7 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 
 	const int cx = 32 * (warp & 3) + lane;         // this thread's tile column
 	const int ry = CW_NVT * (warp >> 2);           // first of its NVT output rows (tile-relative)
+	const int x = x0 + cx;
 	constexpr int NW = CW_NT / 32;
 
 	// packed arms: one warp per tile row, lanes along x (no index division anywhere)
@@ -153,24 +151,15 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 		}
 	}
 
-	for (int dd = 0; dd < dn; dd++) {
-		const int d = d0 + dd;
+	// Disparities whose whole tile lies inside the invalid triangle (x + d*direction outside the image
+	// for every column) form a suffix of the chunk: plain copy, adcensus.cu:353-354, handled last.
+	int nproc = 0;
+	while (nproc < dn && !(direction < 0 ? (x0 + CW_TX - 1 - (d0 + nproc) < 0) : (x0 + d0 + nproc >= W))) nproc++;
+
+	// volume plane tile (+halo) of disparity d into `buf`: cp.async, 4-byte granules (rows of W floats
+	// are only 4-byte aligned), zero-filled outside the image
+	auto issue_tile = [&](int d, float *buf) {
 		const float *plane = vol + (long)d * HW;
-		const int off = (x0 + d * direction) - a1x0;   // sa1 column of tile column 0
-		// whole tile inside the invalid triangle (x + d*direction outside the image for every
-		// column): plain copy, adcensus.cu:353-354 (CTA-uniform, so no barrier is skipped unevenly)
-		if (direction < 0 ? (x0 + CW_TX - 1 - d < 0) : (x0 + d >= W)) {
-			const int x = x0 + cx;
-#pragma unroll
-			for (int oy = 0; oy < CW_NVT; oy++) {
-				const int y = y0 + ry + oy;
-				if (y < H && x < W) out[(long)d * HW + (long)y * W + x] = __ldg(plane + (long)y * W + x);
-			}
-			continue;
-		}
-		__syncthreads();                               // previous plane consumed; arms visible
-		// volume plane tile (+halo): cp.async, 4-byte granules (rows of W floats are only 4-byte
-		// aligned), zero-filled outside the image
 		for (int r = warp; r < TH; r += NW) {
 			const int yy = y0 - R + r;
 			const bool rowok = yy >= 0 && yy < H;
@@ -180,14 +169,33 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 				const int c = lane + 32 * m, xx = x0 - R + c;
 				if (c < TWP) {
 					const bool ok = rowok && xx >= 0 && xx < W;
-					const unsigned dst = (unsigned)__cvta_generic_to_shared(sv + r * TWP + c);
+					const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + r * TWP + c);
 					const int nbytes = ok ? 4 : 0;
 					asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(grow + (ok ? xx : 0)), "r"(nbytes));
 				}
 			}
 		}
+	};
+	// PD = 1 (exact kernel): the tile of disparity dd+1 streams into the other buffer while dd is aggregated
+	constexpr int PD = FAST ? 0 : 1;
+	if (PD == 1 && nproc > 0) {
+		issue_tile(d0, svbuf);
 		asm volatile("cp.async.commit_group;");
-		// combined arms of this disparity (byte-wise min of the left arms at x and the right arms at x + d*dir)
+	}
+	for (int dd = 0; dd < nproc; dd++) {
+		const int d = d0 + dd;
+		const int off = (x0 + d * direction) - a1x0;   // sa1 column of tile column 0
+		const int xs = x + d * direction;
+		const bool valid_col = x < W && xs >= 0 && xs < W;
+		float *sv = svbuf + (PD ? (dd & 1) : 0) * TH * TWP;
+		__syncthreads();                               // previous plane consumed; arms visible
+		if (PD == 1) {
+			if (dd + 1 < nproc) issue_tile(d + 1, svbuf + ((dd + 1) & 1) * TH * TWP);
+		} else {
+			issue_tile(d, sv);
+		}
+		asm volatile("cp.async.commit_group;");
+		// combined arms of this disparity: byte-wise min of the left arms at x and the right arms at x + d*dir
 		for (int r = warp; r < TH; r += NW) {
 #pragma unroll
 			for (int m = 0; m < CW_TX / 32; m++) {
@@ -195,8 +203,38 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 				scomb[r * CW_TX + c] = __vminu4(sa0[r * CW_TX + c], sa1[r * A1W + c + off]);
 			}
 		}
-		asm volatile("cp.async.wait_group 0;");
+		asm volatile("cp.async.wait_group %0;" ::"n"(PD));
 		__syncthreads();
+		if constexpr (FAST) {
+			// exclusive prefix sums of every tile row, accumulated in double, rounded once per entry
+			constexpr int EPL = (TWP + 31) / 32;               // elements per lane
+			for (int r = warp; r < TH; r += NW) {
+				double loc[EPL];
+				double run = 0.0;
+#pragma unroll
+				for (int i = 0; i < EPL; i++) {
+					const int c = lane * EPL + i;
+					float v = c < TWP ? sv[r * TWP + c] : 0.0f;
+					v = v == v ? v : 0.0f;                     // NaN = invalid triangle, never inside a run
+					run += (double)v;
+					loc[i] = run;
+				}
+				double incl = run;                             // inclusive scan of the lane totals
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const double up = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= o) incl += up;
+				}
+				const double base = incl - run;
+#pragma unroll
+				for (int i = 0; i < EPL; i++) {
+					const int c = lane * EPL + i;
+					if (c < TWP) sp[r * PW + c + 1] = (float)(base + loc[i]);
+				}
+				if (lane == 0) sp[r * PW] = 0.0f;
+			}
+			__syncthreads();
+		}
 
 		int U[CW_NVT], Dn[CW_NVT];
 		float acc[CW_NVT], cnt[CW_NVT];
@@ -216,31 +254,50 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 			const int L = c & 255, Rr = (c >> 8) & 255;
 			const float LRf = (float)(L + Rr - 1);             // taps of this row's run (:364-369), exact in fp32
 			float wm[2 * R + 1];
+			float S = 0.0f;
+			if constexpr (FAST) {
+				// sum of the run (x - L, x + Rr): tile columns [cx + R - L + 1, cx + R + Rr)
+				const float *prow = sp + (ry + ri) * PW + cx + R;
+				S = prow[Rr] - prow[1 - L];
+			} else {
 #pragma unroll
-			for (int k = 0; k <= 2 * R; k++) {
-				const float v = wrow[k];
-				// slot inside the run (x - L, x + Rr) (:362-364); the centre slot is, unless the row has no arms (outside the image)
-				wm[k] = k < R ? (L > R - k ? v : 0.0f) : (k > R ? (Rr > k - R ? v : 0.0f) : (L > 0 ? v : 0.0f));
+				for (int k = 0; k <= 2 * R; k++) {
+					// slot inside the run (x - L, x + Rr) (:362-364) keeps its value, the others become +0.0f
+					const float v = wrow[k];
+					wm[k] = k < R ? (L > R - k ? v : 0.0f) : (k > R ? (Rr > k - R ? v : 0.0f) : (L > 0 ? v : 0.0f));
+				}
 			}
 #pragma unroll
 			for (int oy = 0; oy < CW_NVT; oy++) {
 				const int delta = ri - oy - R;                 // row offset from this output's centre row
 				if (delta < -R || delta > R) continue;
-				// row inside this output's vertical arm (:361); centre row iff the output is valid
-				const int va = delta < 0 ? U[oy] : Dn[oy];
-				const int vthr = delta < 0 ? -delta : delta;
-				strip_row<R>(acc[oy], cnt[oy], wm, LRf, va > vthr ? 1.0f : 0.0f);
+				// 1.0f for a row inside this output's vertical arm (:361); the centre row iff the output is valid
+				const float qf = (delta < 0 ? U[oy] > -delta : Dn[oy] > delta) ? 1.0f : 0.0f;
+				if constexpr (FAST) {
+					acc[oy] = fmaf(S, qf, acc[oy]);
+				} else {
+#pragma unroll
+					for (int k = 0; k <= 2 * R; k++) acc[oy] = fmaf(wm[k], qf, acc[oy]);   // :364-367
+				}
+				cnt[oy] = fmaf(LRf, qf, cnt[oy]);                                          // :368
 			}
 		}
-		const int x = x0 + cx;
-		const int xs = x + d * direction;
 #pragma unroll
 		for (int oy = 0; oy < CW_NVT; oy++) {
 			const int y = y0 + ry + oy;
 			if (y >= H || x >= W) continue;
-			float res = (xs < 0 || xs >= W) ? sv[(ry + oy + R) * TWP + cx + R]         // :353-354
-							: acc[oy] / cnt[oy];                        // :373
+			float res = valid_col ? acc[oy] / cnt[oy]                                      // :373
+					      : sv[(ry + oy + R) * TWP + cx + R];                      // :353-354 (keeps NaN)
 			out[(long)d * HW + (long)y * W + x] = res;
+		}
+	}
+	for (int dd = nproc; dd < dn; dd++) {              // tiles entirely inside the invalid triangle
+		const int d = d0 + dd;
+		const float *plane = vol + (long)d * HW;
+#pragma unroll
+		for (int oy = 0; oy < CW_NVT; oy++) {
+			const int y = y0 + ry + oy;
+			if (y < H && x < W) out[(long)d * HW + (long)y * W + x] = __ldg(plane + (long)y * W + x);
 		}
 	}
 }
@@ -354,15 +411,16 @@ __global__ void cbca_generic_kernel(const float *__restrict__ x0c, const float *
 	out[id] = sum / (float)cnt;
 }
 
-template <int R>
+template <int R, bool FAST>
 int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int direction, cudaStream_t s)
 {
 	using Cfg = CWCfg<R>;
+	constexpr int SMEM = FAST ? Cfg::SMEM_FAST : Cfg::SMEM;
 	static bool attr_done[64] = {false};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!attr_done[dev & 63]) {
-		ADC_CUDA(cudaFuncSetAttribute(cbca_win_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+		ADC_CUDA(cudaFuncSetAttribute(cbca_win_kernel<R, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
 		attr_done[dev & 63] = true;
 	}
 	// disparities per CTA.  Measured at 370x1226x228: 4..12 -> 1.01-1.04 ms, 16 -> 1.01 ms, 19 (whole
@@ -373,7 +431,7 @@ int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *
 	if (dch < 1) dch = 1;
 	if (dch > CW_DCH_MAX) dch = CW_DCH_MAX;
 	dim3 grid(adc_div_up(W, CW_TX), adc_div_up(H, CW_TY), adc_div_up(D, dch));
-	cbca_win_kernel<R><<<grid, CW_NT, Cfg::SMEM, s>>>(a0, a1, vol, out, D, H, W, direction, dch);
+	cbca_win_kernel<R, FAST><<<grid, CW_NT, SMEM, s>>>(a0, a1, vol, out, D, H, W, direction, dch);
 	return 0;
 }
 
@@ -387,20 +445,33 @@ void launch_tile(const uint32_t *a0, const uint32_t *a1, const float *vol, float
 }  // namespace
 
 // ---- internal entry points shared with pipeline.cu -------------------------
-int adc_pack_arms(const float *xc, uint32_t *packed, int H, int W, int *maxlen_dev, cudaStream_t s)
+// packed buffer layout (uint32 words, HW = H*W): [image 0 | image 1]
+size_t adc_packed_words(int H, int W) { return 2 * (size_t)H * W; }
+
+int adc_pack_arms(const float *xc, uint32_t *pk, int which, int H, int W, int *maxlen_dev, cudaStream_t s)
 {
-	pack_arms_kernel<<<adc_div_up((long)H * W, 256), 256, 0, s>>>(xc, packed, H, W, maxlen_dev);
+	const long HW = (long)H * W;
+	pack_arms_kernel<<<adc_div_up(HW, 256), 256, 0, s>>>(xc, pk + which * HW, H, W, maxlen_dev);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
 
 // maxlen = longest arm (distance to the exclusive end-point) of either image
-int adc_cbca_packed(const uint32_t *a0, const uint32_t *a1, const float *x0c, const float *x1c,
-		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s)
+// fast != 0 selects the prefix-sum kernel where one exists (arms up to 5 pixels); longer arms always
+// take the exact kernels
+int adc_cbca_packed(const uint32_t *pk, const float *x0c, const float *x1c,
+		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s, int fast)
 {
+	const long HW = (long)H * W;
+	const uint32_t *a0 = pk, *a1 = pk + HW;
 	int halo = maxlen - 1;
-	if (halo <= 1) { int rc = launch_win<1>(a0, a1, vol, out, D, H, W, direction, s); if (rc) return rc; }
-	else if (halo <= 4) { int rc = launch_win<4>(a0, a1, vol, out, D, H, W, direction, s); if (rc) return rc; }
+	if (halo <= 1) {
+		int rc = fast ? launch_win<1, true>(a0, a1, vol, out, D, H, W, direction, s) : launch_win<1, false>(a0, a1, vol, out, D, H, W, direction, s);
+		if (rc) return rc;
+	} else if (halo <= 4) {
+		int rc = fast ? launch_win<4, true>(a0, a1, vol, out, D, H, W, direction, s) : launch_win<4, false>(a0, a1, vol, out, D, H, W, direction, s);
+		if (rc) return rc;
+	}
 	else if (halo <= 8) launch_tile<8>(a0, a1, vol, out, D, H, W, direction, s);
 	else if (halo <= 13) launch_tile<13>(a0, a1, vol, out, D, H, W, direction, s);
 	else {
@@ -419,14 +490,14 @@ extern "C" int mccnn_pack_arms(const float *x0c, const float *x1c, void *packed,
 	cudaStream_t s = adc_stream(stream);
 	uint32_t *pk = (uint32_t *)packed;
 	const long HW = (long)H * W;
-	int *maxlen_dev = (int *)(pk + 2 * HW);
+	int *maxlen_dev = (int *)(pk + adc_packed_words(H, W));
 	int rc = (int)cudaMemsetAsync(maxlen_dev, 0, sizeof(int), s);
-	if (!rc) rc = adc_pack_arms(x0c, pk, H, W, maxlen_dev, s);
-	if (!rc) rc = adc_pack_arms(x1c, pk + HW, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_pack_arms(x0c, pk, 0, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_pack_arms(x1c, pk, 1, H, W, maxlen_dev, s);
 	return rc;
 }
 
-extern "C" size_t mccnn_packed_arms_bytes(int H, int W) { return (2 * (size_t)H * W + 1) * sizeof(uint32_t); }
+extern "C" size_t mccnn_packed_arms_bytes(int H, int W) { return (adc_packed_words(H, W) + 1) * sizeof(uint32_t); }
 
 extern "C" int mccnn_cbca_packed(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 				 int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream)
@@ -434,7 +505,18 @@ extern "C" int mccnn_cbca_packed(const void *packed, const float *x0c, const flo
 	if (!packed || !x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
 	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1) || max_arm < 1) return ADCENSUS_EINVAL;
 	const uint32_t *pk = (const uint32_t *)packed;
-	return adc_cbca_packed(pk, pk + (long)H * W, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, adc_stream(stream));
+	return adc_cbca_packed(pk, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, adc_stream(stream), 0);
+}
+
+// Opt-in approximate aggregation (prefix sums per support row; same region and row order, different
+// rounding: ~1e-6 relative to the exact kernel, NaN positions identical).  Not bit-exact with the reference.
+extern "C" int mccnn_cbca_packed_fast(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+				      int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream)
+{
+	if (!packed || !x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
+	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1) || max_arm < 1) return ADCENSUS_EINVAL;
+	const uint32_t *pk = (const uint32_t *)packed;
+	return adc_cbca_packed(pk, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, adc_stream(stream), 1);
 }
 
 extern "C" int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1, adcensus_stream_t stream)
@@ -454,13 +536,13 @@ extern "C" int adcensus_cbca_ex(const float *x0c, const float *x1c, const float 
 	cudaStream_t s = adc_stream(stream);
 	long HW = (long)H * W;
 	uint32_t *packed = nullptr;
-	int rc = adc_scratch_alloc((void **)&packed, (2 * HW + 1) * sizeof(uint32_t), s);
+	int rc = adc_scratch_alloc((void **)&packed, (adc_packed_words(H, W) + 1) * sizeof(uint32_t), s);
 	if (rc) return rc;
-	int *maxlen_dev = (int *)(packed + 2 * HW);
+	int *maxlen_dev = (int *)(packed + adc_packed_words(H, W));
 	rc = (int)cudaMemsetAsync(maxlen_dev, 0, sizeof(int), s);
-	if (!rc) rc = adc_pack_arms(x0c, packed, H, W, maxlen_dev, s);
-	if (!rc) rc = adc_pack_arms(x1c, packed + HW, H, W, maxlen_dev, s);
-	if (!rc) rc = adc_cbca_packed(packed, packed + HW, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, s);
+	if (!rc) rc = adc_pack_arms(x0c, packed, 0, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_pack_arms(x1c, packed, 1, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_cbca_packed(packed, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, s, 0);
 	int rc2 = adc_scratch_free(packed, s);
 	return rc ? rc : rc2;
 }
@@ -473,16 +555,16 @@ extern "C" int adcensus_cbca(const float *x0c, const float *x1c, const float *vo
 	cudaStream_t s = adc_stream(stream);
 	long HW = (long)H * W;
 	uint32_t *packed = nullptr;
-	int rc = adc_scratch_alloc((void **)&packed, (2 * HW + 1) * sizeof(uint32_t), s);
+	int rc = adc_scratch_alloc((void **)&packed, (adc_packed_words(H, W) + 1) * sizeof(uint32_t), s);
 	if (rc) return rc;
-	int *maxlen_dev = (int *)(packed + 2 * HW);
+	int *maxlen_dev = (int *)(packed + adc_packed_words(H, W));
 	int maxlen = 0;
 	rc = (int)cudaMemsetAsync(maxlen_dev, 0, sizeof(int), s);
-	if (!rc) rc = adc_pack_arms(x0c, packed, H, W, maxlen_dev, s);
-	if (!rc) rc = adc_pack_arms(x1c, packed + HW, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_pack_arms(x0c, packed, 0, H, W, maxlen_dev, s);
+	if (!rc) rc = adc_pack_arms(x1c, packed, 1, H, W, maxlen_dev, s);
 	if (!rc) rc = (int)cudaMemcpyAsync(&maxlen, maxlen_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
 	if (!rc) rc = (int)cudaStreamSynchronize(s);
-	if (!rc) rc = adc_cbca_packed(packed, packed + HW, x0c, x1c, vol_in, vol_out, D, H, W, direction, maxlen, s);
+	if (!rc) rc = adc_cbca_packed(packed, x0c, x1c, vol_in, vol_out, D, H, W, direction, maxlen, s, 0);
 	int rc2 = adc_scratch_free(packed, s);
 	return rc ? rc : rc2;
 }

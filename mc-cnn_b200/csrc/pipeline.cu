@@ -14,9 +14,10 @@
 #include "common.cuh"
 
 // internal entry points of the other translation units
-int adc_pack_arms(const float *xc, uint32_t *packed, int H, int W, int *maxlen_dev, cudaStream_t s);
-int adc_cbca_packed(const uint32_t *a0, const uint32_t *a1, const float *x0c, const float *x1c,
-		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s);
+size_t adc_packed_words(int H, int W);
+int adc_pack_arms(const float *xc, uint32_t *pk, int which, int H, int W, int *maxlen_dev, cudaStream_t s);
+int adc_cbca_packed(const uint32_t *pk, const float *x0c, const float *x1c,
+		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s, int fast);
 size_t adc_sgm_table_bytes(int H, int W, int D);
 int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, uint8_t *tab, int H, int W, int D,
 	     float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
@@ -28,12 +29,13 @@ struct mccnn_pipeline {
 	long HW, V;
 	size_t bytes;
 	int launches;
+	int fast_cbca;   // opt-in approximate CBCA (mccnn_pipeline_set_fast_cbca); 0 = exact (default)
 	// device buffers
 	float *vols;      // 2V: [0] left volume, [1] right volume (main.lua:946)
 	float *bufA;      // V : CBCA ping-pong / SGM transposed input
 	float *bufC;      // V : SGM accumulator (H,W,D)
 	float *x0c, *x1c; // 4HW each: cross arms (main.lua:993-996)
-	uint32_t *packed; // 2HW: packed arm lengths
+	uint32_t *packed; // packed arm lengths of both images (adc_packed_words)
 	int *maxlen;
 	float *maps;      // 8HW: disparity maps and stage outputs
 	float *gauss;     // ks*ks
@@ -85,7 +87,7 @@ extern "C" int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, 
 	if (!rc) rc = dev_alloc((void **)&p->bufC, p->V * f, &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->x0c, 4 * p->HW * f, &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->x1c, 4 * p->HW * f, &p->bytes);
-	if (!rc) rc = dev_alloc((void **)&p->packed, 2 * p->HW * sizeof(uint32_t), &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->packed, adc_packed_words(H, W) * sizeof(uint32_t), &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->maxlen, sizeof(int), &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->maps, 8 * p->HW * f, &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->sgmtab, adc_sgm_table_bytes(H, W, D), &p->bytes);
@@ -124,6 +126,7 @@ extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
 }
 
 extern "C" size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p) { return p ? p->bytes : 0; }
+extern "C" void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on) { if (p) p->fast_cbca = on ? 1 : 0; }
 extern "C" int mccnn_pipeline_launches_per_run(const mccnn_pipeline *p) { return p ? p->launches : 0; }
 
 #define STEP(call)                 \
@@ -154,8 +157,8 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 	const int maxlen = o.L1 > 2 ? o.L1 : 2;  // bound on the arm length cross() can produce
 	STEP(adcensus_cross(imgL, p->x0c, H, W, o.L1, o.tau1, s));
 	STEP(adcensus_cross(imgR, p->x1c, H, W, o.L1, o.tau1, s));
-	STEP(adc_pack_arms(p->x0c, p->packed, H, W, p->maxlen, s));
-	STEP(adc_pack_arms(p->x1c, p->packed + HW, H, W, p->maxlen, s)); nl += 4;
+	STEP(adc_pack_arms(p->x0c, p->packed, 0, H, W, p->maxlen, s));
+	STEP(adc_pack_arms(p->x1c, p->packed, 1, H, W, p->maxlen, s)); nl += 4;
 
 	float *dispR = p->maps, *dispL = p->maps + HW;
 	float *final_left = nullptr;
@@ -165,7 +168,7 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 		const int direction = directions[k];
 		float *cur = direction == -1 ? volsL : volsR;                                            // :986
 		for (int i = 0; i < o.cbca_i1; i++) {                                                    // :998-1001
-			STEP(adc_cbca_packed(p->packed, p->packed + HW, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, s));
+			STEP(adc_cbca_packed(p->packed, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, s, p->fast_cbca));
 			float *t = cur; cur = spare; spare = t; nl += 1;
 		}
 		for (int it = 0; it < o.sgm_i; it++) {                                                   // :1008-1020
@@ -176,7 +179,7 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 			nl += 7;
 		}
 		for (int i = 0; i < o.cbca_i2; i++) {                                                    // :1035-1038
-			STEP(adc_cbca_packed(p->packed, p->packed + HW, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, s));
+			STEP(adc_cbca_packed(p->packed, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, s, p->fast_cbca));
 			float *t = cur; cur = spare; spare = t; nl += 1;
 		}
 		STEP(mccnn_argmin(cur, direction == 1 ? dispR : dispL, D, (int)HW, s)); nl += 1;         // :1049-1050

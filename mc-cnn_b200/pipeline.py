@@ -153,6 +153,11 @@ class StereoPipeline:
         except Exception:
             pass
 
+    def set_fast_cbca(self, on=True):
+        """Opt in to the approximate CBCA kernel (prefix sums per support row: ~1e-6 relative to the
+        exact-order kernel, not bit-exact with the reference).  Default is exact."""
+        adcensus.lib().mccnn_pipeline_set_fast_cbca(self._h, int(bool(on)))
+
     @property
     def device_bytes(self):
         return adcensus.lib().mccnn_pipeline_device_bytes(self._h)

@@ -351,6 +351,36 @@ def test_full_size_against_live_reference(H, W, C, D, preset, over):
     sp.close()
 
 
+def test_fast_cbca_mode_is_within_tolerance(oracle):
+    """The opt-in prefix-sum CBCA is NOT bit-exact: volumes must agree with the oracle within the north
+    star's 1e-4 (they do to ~1e-6), NaN positions exactly, and the final disparity map may differ only
+    at isolated near-tie pixels."""
+    H, W, C, D = 96, 200, 16, 40
+    opt = pipeline.make_params("kitti", "accurate_cbca4")
+    p = synth.make_pair(H, W, C, D, seed=4)
+    want, wL, wR = oracle.stereo_predict(p["featL"], p["featR"], p["imgL"], p["imgR"], D,
+                                         oracle.Params(**opt.as_dict()), want_vols=True)
+    t = lambda a: cu(a)
+    sp = pipeline.StereoPipeline(C, D, H, W, opt)
+    sp.set_fast_cbca(True)
+    volL = torch.empty((D, H, W), device=dev())
+    volR = torch.empty((D, H, W), device=dev())
+    disp = sp.run(t(p["featL"]), t(p["featR"]), t(p["imgL"]), t(p["imgR"]), volL=volL, volR=volR)
+    for got, ref, what in ((volL, wL, "left.bin"), (volR, wR, "right.bin")):
+        g = got.cpu().numpy()
+        assert np.array_equal(np.isnan(g), np.isnan(ref)), what + ": NaN pattern differs"
+        m = ~np.isnan(ref)
+        err = np.abs(g[m] - ref[m]) / np.maximum(1.0, np.abs(ref[m]))
+        assert err.max() <= 1e-4, "%s: max relative error %.3g above 1e-4" % (what, err.max())
+    d = disp.cpu().numpy()
+    frac = float((np.abs(d - want) > 1e-4 * np.maximum(1.0, np.abs(want))).mean())
+    assert frac < 5e-3, "fast CBCA changed %.4f of the disparity map" % frac
+    # the default (exact) mode stays bit-identical
+    sp.set_fast_cbca(False)
+    same(sp.run(t(p["featL"]), t(p["featR"]), t(p["imgL"]), t(p["imgR"])), want, "exact mode after toggling")
+    sp.close()
+
+
 def test_lua_face_through_the_reference_driver(oracle):
     """luaopen_libadcensus of OUR library (shim build), called by the very driver that calls the
     reference's: same 31 names, same positional signatures, same results."""
