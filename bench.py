@@ -248,7 +248,7 @@ def cpu_baseline(cfg, opt):
     from mccnn_b200 import synth
     from oracle import oracle as orc
 
-    rows = min(cfg["H"], 48)
+    rows = min(cfg["H"], 96)
     p = synth.make_pair(rows, cfg["W"], cfg["C"], cfg["D"], seed=5)
     op = orc.Params(**opt.as_dict())
     orc.lib()
@@ -356,10 +356,15 @@ def run_b200(args):
         dom = max(share, key=share.get)
         peak, peak_src = load_peaks()
 
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic_k228.json")
+        if args.workload == "k228" and not args.small and os.path.exists(tpath):
+            traffic = json.load(open(tpath))
+
         def roof(name):
             ach = ab[name] / (stages[name] * 1e-3) / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(ach / peak, 4), "traffic": traffic.get(name), "peak_source": peak_src,
                     "algorithmic_bytes": ab[name], "ms": round(stages[name], 4)}
 
         out = {
