@@ -180,6 +180,7 @@ def time_op(fn, iters, flush):
     """average CUDA-event duration (ms) of fn() on torch's current stream, L2 flushed before each"""
     import torch
 
+    fn()            # untimed: lazy kernel load, pool growth
     evs = []
     for _ in range(iters):
         flush()

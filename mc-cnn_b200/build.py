@@ -16,7 +16,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libadcensus_b200.so")
 SOURCES = ["common.cu", "stereo_join.cu", "cross_cbca.cu", "sgm.cu", "post.cu", "pipeline.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "--compiler-options", "-fPIC", "-I" + INCLUDE, "-I" + CSRC]
+NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-diag-suppress", "177", "-std=c++17", "--compiler-options", "-fPIC", "-I" + INCLUDE, "-I" + CSRC]
 
 
 def _nvcc():

@@ -143,178 +143,316 @@ __device__ __forceinline__ void store_vec(const float (&r)[K], float *p, int dba
 }
 
 // ---------------------------------------------------------------- one scan direction
-// SD: 0 right, 1 left, 2 down, 3 up (adcensus.cu:541-565).  ZERO: output known to be 0 on entry.
-// NR: scanlines per warp.  A horizontal scan has only H (370) lines of W (1226) strictly serial
-// steps, one warp per SM sub-partition; interleaving NR = 2 independent lines in one warp fills the
-// dependent-issue bubbles of the recurrence (min tree -> CREDUX -> fminf chain).
-template <int K, bool VEC, int SD, bool ZERO, int PF, int WPB, int NR>
+
+// State of one warp scanning one line.  SD: 0 right, 1 left, 2 down, 3 up (adcensus.cu:541-565).
+template <int K, bool VEC, int SD, int PF>
+struct SgmScan {
+	static constexpr int VSZ = 32 * K;             // floats per cost vector slot (padded to 32*K)
+	static constexpr int dx = SD == 0 ? 1 : (SD == 1 ? -1 : 0);
+	static constexpr int dy = SD == 2 ? 1 : (SD == 3 ? -1 : 0);
+	static constexpr int tshift_x = dx < 0 ? 1 : 0;
+	static constexpr int tshift_y = dy < 0 ? 1 : 0;
+	// How a lane gets the D2 classes of its K slots (bytes at consecutive table columns):
+	//  SLIDE  horizontal scans: the K bytes of step s+1 are those of step s moved by one slot, so a
+	//         register window is shifted and ONE new byte is loaded per step, three steps ahead;
+	//  WORDS  vertical scans: K new bytes per step, fetched one step ahead as K/4+1 aligned words
+	//         and funnel-shifted into place when consumed;
+	//  else   (K < 4) one byte load per slot, one step ahead.
+	// Nothing touches a loaded value in the step that issues the load (the table row changes every
+	// step of a vertical scan, so these loads miss L1; consumed just in time they were the top stall).
+	static constexpr bool SLIDE = SD < 2 && K % 4 == 0;
+	static constexpr bool WORDS = SD >= 2 && K % 4 == 0;
+	static constexpr int NWD = (K + 3) / 4;        // class window registers, 4 slots each
+	static constexpr int NRAW = K / 4 + 1;
+
+	const float *in;
+	float *out;
+	float *ring;                                   // this lane's K floats of slot 0: [PF][2][VSZ] (in, out)
+	const uint8_t *t1, *t2;                        // D1 / D2 class planes, at image column xoff
+	int lane, dbase, D, Wp, Ht, W, yoff, ddir;
+	long pix_step;
+	float P1f, P2f, P1s, P2s, P1m, P2m, P1f_a, P1s_a, P1m_a;
+	int x, y;                                      // pixel of the NEXT step to execute
+	long base;
+	float prev[K];
+	unsigned cw[NWD], c1c;                         // classes of the step being executed; byte k%4 of cw[k/4] = slot k
+	unsigned nw[NWD], q1, q2, c1q[3];              // SLIDE: next window, entering bytes, D1 classes ahead
+	const uint8_t *pe, *p1;
+	int xl;
+	bool up;
+	unsigned raw[NRAW], cb[K], c1n;                // WORDS / byte path: classes of the next step
+	int rsh;
+
+	__device__ __forceinline__ void init(const uint8_t *tab, const float *in_, float *out_, float *ring_, int H, int W_, int D_,
+					      int pad, const SgmParams &prm, int line)
+	{
+		in = in_; out = out_; ring = ring_;
+		lane = threadIdx.x & 31;
+		dbase = lane * K;
+		D = D_;
+		W = W_;
+		// adcensus.cu:595-605 and :609/:612, same expressions
+		P1f = prm.pi1; P2f = prm.pi2;
+		P1s = prm.pi1 / (prm.q1 * prm.q2); P2s = prm.pi2 / (prm.q1 * prm.q2);
+		P1m = prm.pi1 / prm.q1; P2m = prm.pi2 / prm.q1;
+		P1f_a = P1f / prm.alpha1; P1s_a = P1s / prm.alpha1; P1m_a = P1m / prm.alpha1;
+		// class tables: D1 from plane (SD<2 ? 0 : 1), D2 from plane (SD<2 ? 2 : 3).  The stored
+		// difference at (y, j) pairs pixel j with its left / upper neighbour, so scans that look
+		// right / down (dx = -1, dy = -1) read the entry one further.
+		Wp = prm.Wt + 2 * pad;
+		Ht = prm.Ht; yoff = prm.yoff; ddir = prm.direction;
+		const long plane = (long)prm.Ht * Wp;
+		t1 = tab + (SD < 2 ? 0 : 1) * plane + pad + prm.xoff;
+		t2 = tab + (SD < 2 ? 2 : 3) * plane + pad + prm.xoff;
+		x = SD == 0 ? 0 : (SD == 1 ? W - 1 : line);
+		y = SD == 2 ? 0 : (SD == 3 ? H - 1 : line);
+		pix_step = (long)(dy * W + dx) * D;
+		base = ((long)y * W + x) * D + dbase;
+		// NaN in the padding slots of the ring (never overwritten)
+#pragma unroll
+		for (int s = 0; s < PF * 2; s++)
+#pragma unroll
+			for (int k = 0; k < K; k++) ring[s * VSZ + k] = adc_nan();
+		cls_prime(x + dx, y + dy);                     // step 0 uses no penalties
+	}
+
+	__device__ __forceinline__ int clampx(int xs) const { return min(max(xs, 0), W - 1); }
+
+	// D1 class (:587) and D2 classes (:588-594) of pixel (xs, ys), the first recurrence step
+	__device__ __forceinline__ void cls_prime(int xs, int ys)
+	{
+		if constexpr (SLIDE) {
+			const int ty = min(max(ys + yoff, 0), Ht - 1);
+			const uint8_t *r2 = t2 + (long)ty * Wp + tshift_x;
+			p1 = t1 + (long)ty * Wp + tshift_x;
+			up = dx * ddir < 0;                        // slot k of the next step = slot k-1 of this one
+			pe = r2 + (dbase + (up ? 0 : K - 1)) * ddir;
+#pragma unroll
+			for (int i = 0; i < NWD; i++) nw[i] = 0;
+#pragma unroll
+			for (int k = 0; k < K; k++)
+				nw[k / 4] |= (unsigned)__ldg(r2 + clampx(xs) + (dbase + k) * ddir) << (8 * (k & 3));
+			c1q[0] = __ldg(p1 + clampx(xs));
+			c1q[1] = __ldg(p1 + clampx(xs + dx));
+			c1q[2] = __ldg(p1 + clampx(xs + 2 * dx));
+			q1 = __ldg(pe + clampx(xs + dx));
+			q2 = __ldg(pe + clampx(xs + 2 * dx));
+			xl = xs + 3 * dx;
+		} else {
+			cls_fetch(xs, ys);
+		}
+	}
+
+	__device__ __forceinline__ void cls_fetch(int xs, int ys)
+	{
+		const int ty = min(max(ys + yoff + tshift_y, 0), Ht - 1);           // image row of the stored difference
+		const uint8_t *q = t2 + (long)ty * Wp + xs + tshift_x + dbase * ddir;
+		c1n = __ldg(t1 + (long)ty * Wp + xs + tshift_x);
+		if constexpr (WORDS) {
+			const uintptr_t lo = (uintptr_t)(ddir > 0 ? q : q - (K - 1));   // lowest address of the K bytes
+			rsh = (int)(lo & 3) * 8;
+			const unsigned *al = reinterpret_cast<const unsigned *>(lo & ~(uintptr_t)3);
+#pragma unroll
+			for (int i = 0; i < NRAW; i++) raw[i] = __ldg(al + i);
+		} else {
+#pragma unroll
+			for (int k = 0; k < K; k++) cb[k] = __ldg(q + k * ddir);
+		}
+	}
+
+	// classes of the step about to execute -> (c1c, cw); start the loads for later steps
+	__device__ __forceinline__ void cls_take()
+	{
+		if constexpr (SLIDE) {
+#pragma unroll
+			for (int i = 0; i < NWD; i++) cw[i] = nw[i];
+			c1c = c1q[0];
+			if (up) {
+#pragma unroll
+				for (int i = NWD - 1; i > 0; i--) nw[i] = __funnelshift_l(nw[i - 1], nw[i], 8);
+				nw[0] = (nw[0] << 8) | q1;
+			} else {
+#pragma unroll
+				for (int i = 0; i < NWD - 1; i++) nw[i] = __funnelshift_r(nw[i], nw[i + 1], 8);
+				nw[NWD - 1] = (nw[NWD - 1] >> 8) | (q1 << 24);
+			}
+			q1 = q2;
+			c1q[0] = c1q[1];
+			c1q[1] = c1q[2];
+			const int xc = clampx(xl);
+			q2 = __ldg(pe + xc);
+			c1q[2] = __ldg(p1 + xc);
+			xl += dx;
+		} else {
+			c1c = c1n;
+			if constexpr (WORDS) {
+				unsigned w[K / 4];
+#pragma unroll
+				for (int i = 0; i < K / 4; i++) w[i] = __funnelshift_r(raw[i], raw[i + 1], rsh);
+#pragma unroll
+				for (int i = 0; i < K / 4; i++) cw[i] = ddir > 0 ? w[i] : __byte_perm(w[K / 4 - 1 - i], 0, 0x0123);
+			} else {
+				cw[0] = 0;
+#pragma unroll
+				for (int k = 0; k < K; k++) cw[0] |= cb[k] << (8 * k);
+			}
+			cls_fetch(x + dx, y + dy);                 // for the step after this one
+		}
+	}
+
+	// steps [s_begin, s_end) of the scan; use_out: read-modify-write the accumulator (else it is
+	// known to hold zeros).  Streams the cost (and accumulator) vectors of the next PF pixels into
+	// the shared-memory ring with cp.async; every lane fetches exactly the elements it consumes.
+	__device__ __forceinline__ void run(int s_begin, int s_end, bool use_out)
+	{
+#pragma unroll
+		for (int u = 0; u < PF; u++) {
+			if (s_begin + u < s_end) {
+				issue_vec<K, VEC>(ring + (u * 2) * VSZ, in + base + u * pix_step, dbase, D);
+				if (use_out) issue_vec<K, VEC>(ring + (u * 2 + 1) * VSZ, out + base + u * pix_step, dbase, D);
+			}
+			asm volatile("cp.async.commit_group;");
+		}
+		int slot = 0;
+#pragma unroll 1
+		for (int s = s_begin; s < s_end; s++) {
+			float *rs = ring + slot * (2 * VSZ);
+			slot = slot + 1 == PF ? 0 : slot + 1;
+			asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1));
+			float cin[K], cout[K];
+			read_slot<K>(cin, rs);
+			if (use_out) read_slot<K>(cout, rs + VSZ);
+
+			float val[K];
+			if (s == 0) {                                   // adcensus.cu:567-572
+#pragma unroll
+				for (int k = 0; k < K; k++) val[k] = cin[k];
+			} else {
+				float mt[K];
+#pragma unroll
+				for (int k = 0; k < K; k++) mt[k] = prev[k];
+#pragma unroll
+				for (int w = K / 2; w > 0; w >>= 1)
+#pragma unroll
+					for (int k = 0; k < w; k++) mt[k] = fminf(mt[k], mt[k + w]);
+				const float m = warp_min_f32(mt[0]);            // :579-584
+				float left = __shfl_up_sync(0xffffffffu, prev[K - 1], 1);
+				float right = __shfl_down_sync(0xffffffffu, prev[0], 1);
+				if (lane == 0) left = adc_nan();                // d - 1 < 0 (:608)
+				if (lane == 31) right = adc_nan();
+
+				cls_take();
+				// penalties when the D2 class equals the D1 class (both < tau or both > tau), else middle
+				const unsigned c1 = c1c;
+				const bool c1lt = c1 == 0;
+				const float P1e = c1 == 1 ? P1m : (c1lt ? P1f : P1s);
+				const float P2e = c1 == 1 ? P2m : (c1lt ? P2f : P2s);
+				const float P1ae = c1 == 1 ? P1m_a : (c1lt ? P1f_a : P1s_a);
+				unsigned xw[NWD];
+#pragma unroll
+				for (int i = 0; i < NWD; i++) xw[i] = cw[i] ^ (c1 * 0x01010101u);
+#pragma unroll
+				for (int k = 0; k < K; k++) {
+					const bool eq = (xw[k / 4] & (0xffu << (8 * (k & 3)))) == 0;
+					const float P1 = eq ? P1e : P1m, P2 = eq ? P2e : P2m, P1a = eq ? P1ae : P1m_a;
+					const float pm = k > 0 ? prev[k - 1] : left;
+					const float pp = k < K - 1 ? prev[k + 1] : right;
+					float cost = fminf(prev[k], m + P2);                               // :607
+					cost = fminf(cost, pm + (SD == 2 ? P1a : P1));                     // :609
+					cost = fminf(cost, pp + (SD == 3 ? P1a : P1));                     // :612
+					val[k] = cin[k] + cost - m;                                        // :615
+				}
+			}
+			float o[K];
+#pragma unroll
+			for (int k = 0; k < K; k++) {
+				o[k] = (use_out ? cout[k] : 0.0f) + val[k];                            // :569 / :616
+				prev[k] = val[k];                                                      // :570 / :617
+			}
+			store_vec<K, VEC>(o, out + base, dbase, D);
+			// refill this ring slot with step s + PF (its values are in registers by now)
+			if (s + PF < s_end) {
+				issue_vec<K, VEC>(rs, in + base + PF * pix_step, dbase, D);
+				if (use_out) issue_vec<K, VEC>(rs + VSZ, out + base + PF * pix_step, dbase, D);
+			}
+			asm volatile("cp.async.commit_group;");
+			base += pix_step;
+			x += dx;
+			y += dy;
+		}
+		asm volatile("cp.async.wait_group 0;");
+	}
+};
+
+// One launch = one direction: one warp per scanline.  ZERO: output known to be 0 on entry.
+template <int K, bool VEC, int SD, bool ZERO, int PF, int WPB>
 __global__ void __launch_bounds__(32 * WPB)
 sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, float *__restrict__ out,
 		int H, int W, int D, int pad, SgmParams prm)
 {
 	extern __shared__ __align__(16) float sgm_smem[];
-	constexpr int VSZ = 32 * K;                    // floats per cost vector slot (padded to 32*K)
-	constexpr int NV = ZERO ? 1 : 2;               // ring holds `in` (and `out` unless ZERO)
-	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const int line0 = (blockIdx.x * WPB + wib) * NR;
-	const int nlines = SD < 2 ? H : W;
-	const int nsteps = SD < 2 ? W : H;
-	if (line0 >= nlines) return;                   // whole warp
-
-	constexpr int dx = SD == 0 ? 1 : (SD == 1 ? -1 : 0);
-	constexpr int dy = SD == 2 ? 1 : (SD == 3 ? -1 : 0);
-	const int dbase = lane * K;
-	float *ring = sgm_smem + (size_t)wib * NR * PF * NV * VSZ + dbase;   // this lane's K floats of slot 0
-
-	// adcensus.cu:595-605 and :609/:612, same expressions
-	const float P1f = prm.pi1, P2f = prm.pi2;
-	const float P1s = prm.pi1 / (prm.q1 * prm.q2), P2s = prm.pi2 / (prm.q1 * prm.q2);
-	const float P1m = prm.pi1 / prm.q1, P2m = prm.pi2 / prm.q1;
-	const float P1f_a = P1f / prm.alpha1, P1s_a = P1s / prm.alpha1, P1m_a = P1m / prm.alpha1;
-
-	// class tables: D1 from plane (SD<2 ? 0 : 1), D2 from plane (SD<2 ? 2 : 3).  The stored
-	// difference at (y, j) pairs pixel j with its left / upper neighbour, so scans that look
-	// right / down (dx = -1, dy = -1) read the entry one further.
-	const int Wp = prm.Wt + 2 * pad;
-	const long plane = (long)prm.Ht * Wp;
-	const uint8_t *t1 = tab + (SD < 2 ? 0 : 1) * plane + pad + prm.xoff;
-	const uint8_t *t2 = tab + (SD < 2 ? 2 : 3) * plane + pad + prm.xoff;
-	constexpr int tshift_x = dx < 0 ? 1 : 0;
-	constexpr int tshift_y = dy < 0 ? 1 : 0;
-	const int ddir = prm.direction;
-	const long pix_step = (long)(dy * W + dx) * D;
-
-	bool live[NR];
-	int x[NR], y[NR];
-	long base[NR];
-	float *rg[NR];
-#pragma unroll
-	for (int r = 0; r < NR; r++) {
-		const int line = line0 + r;
-		live[r] = line < nlines;                   // warp-uniform
-		const int ln = live[r] ? line : line0;
-		x[r] = SD == 0 ? 0 : (SD == 1 ? W - 1 : ln);
-		y[r] = SD == 2 ? 0 : (SD == 3 ? H - 1 : ln);
-		base[r] = ((long)y[r] * W + x[r]) * D + dbase;
-		rg[r] = ring + r * PF * NV * VSZ;
-	}
-
-	// NaN in the padding slots (never overwritten), then fill the ring
-#pragma unroll
-	for (int s = 0; s < NR * PF * NV; s++)
-#pragma unroll
-		for (int k = 0; k < K; k++) ring[s * VSZ + k] = adc_nan();
-#pragma unroll
-	for (int u = 0; u < PF; u++) {
-#pragma unroll
-		for (int r = 0; r < NR; r++)
-			if (live[r] && u < nsteps) {
-				issue_vec<K, VEC>(rg[r] + (u * NV) * VSZ, in + base[r] + u * pix_step, dbase, D);
-				if (!ZERO) issue_vec<K, VEC>(rg[r] + (u * NV + 1) * VSZ, out + base[r] + u * pix_step, dbase, D);
-			}
-		asm volatile("cp.async.commit_group;");
-	}
-
-	// penalty classes are fetched one step ahead (the row of the table changes every step of a
-	// vertical scan, so these loads miss L1; fetched just in time they were the top stall)
-	uint8_t c1n[NR], c2n[NR][K];
-	auto fetch_classes = [&](int r, int xs, int ys) {
-		const int ty = min(max(ys + prm.yoff + tshift_y, 0), prm.Ht - 1);   // image row of the stored difference
-		const uint8_t *q = t2 + (long)ty * Wp + xs + tshift_x + dbase * ddir;  // D2 classes (:588-594)
-		c1n[r] = __ldg(t1 + (long)ty * Wp + xs + tshift_x);                     // D1 class (:587)
-#pragma unroll
-		for (int k = 0; k < K; k++) c2n[r][k] = __ldg(q + k * ddir);
-	};
-#pragma unroll
-	for (int r = 0; r < NR; r++) fetch_classes(r, x[r] + dx, y[r] + dy);      // for step 1
-
-	float prev[NR][K];
-	for (int s0 = 0; s0 < nsteps; s0 += PF) {
-#pragma unroll
-		for (int u = 0; u < PF; u++) {
-			const int s = s0 + u;
-			if (s >= nsteps) break;
-			asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1));
-#pragma unroll
-			for (int r = 0; r < NR; r++) {
-				if (!live[r]) continue;
-				float cin[K], cout[K];
-				read_slot<K>(cin, rg[r] + (u * NV) * VSZ);
-				if (!ZERO) read_slot<K>(cout, rg[r] + (u * NV + 1) * VSZ);
-
-				float val[K];
-				if (s == 0) {                                   // adcensus.cu:567-572
-#pragma unroll
-					for (int k = 0; k < K; k++) val[k] = cin[k];
-				} else {
-					float mt[K];
-#pragma unroll
-					for (int k = 0; k < K; k++) mt[k] = prev[r][k];
-#pragma unroll
-					for (int w = K / 2; w > 0; w >>= 1)
-#pragma unroll
-						for (int k = 0; k < w; k++) mt[k] = fminf(mt[k], mt[k + w]);
-					const float m = warp_min_f32(mt[0]);            // :579-584
-					float left = __shfl_up_sync(0xffffffffu, prev[r][K - 1], 1);
-					float right = __shfl_down_sync(0xffffffffu, prev[r][0], 1);
-					if (lane == 0) left = adc_nan();                // d - 1 < 0 (:608)
-					if (lane == 31) right = adc_nan();
-
-					const uint8_t c1 = c1n[r];
-					uint8_t c2[K];
-#pragma unroll
-					for (int k = 0; k < K; k++) c2[k] = c2n[r][k];
-					fetch_classes(r, x[r] + dx, y[r] + dy);         // for step s + 1
-					// penalties when the D2 class equals the D1 class (both < tau or both > tau), else middle
-					const bool c1lt = c1 == 0;
-					const float P1e = c1 == 1 ? P1m : (c1lt ? P1f : P1s);
-					const float P2e = c1 == 1 ? P2m : (c1lt ? P2f : P2s);
-					const float P1ae = c1 == 1 ? P1m_a : (c1lt ? P1f_a : P1s_a);
-#pragma unroll
-					for (int k = 0; k < K; k++) {
-						const bool eq = c2[k] == c1;
-						const float P1 = eq ? P1e : P1m, P2 = eq ? P2e : P2m, P1a = eq ? P1ae : P1m_a;
-						const float pm = k > 0 ? prev[r][k - 1] : left;
-						const float pp = k < K - 1 ? prev[r][k + 1] : right;
-						float cost = fminf(prev[r][k], m + P2);                            // :607
-						cost = fminf(cost, pm + (SD == 2 ? P1a : P1));                     // :609
-						cost = fminf(cost, pp + (SD == 3 ? P1a : P1));                     // :612
-						val[k] = cin[k] + cost - m;                                        // :615
-					}
-				}
-				float o[K];
-#pragma unroll
-				for (int k = 0; k < K; k++) {
-					o[k] = (ZERO ? 0.0f : cout[k]) + val[k];                               // :569 / :616
-					prev[r][k] = val[k];                                                   // :570 / :617
-				}
-				store_vec<K, VEC>(o, out + base[r], dbase, D);
-				// refill this ring slot with step s + PF (its values are in registers by now)
-				if (s + PF < nsteps) {
-					issue_vec<K, VEC>(rg[r] + (u * NV) * VSZ, in + base[r] + PF * pix_step, dbase, D);
-					if (!ZERO) issue_vec<K, VEC>(rg[r] + (u * NV + 1) * VSZ, out + base[r] + PF * pix_step, dbase, D);
-				}
-				base[r] += pix_step;
-				x[r] += dx;
-				y[r] += dy;
-			}
-			asm volatile("cp.async.commit_group;");
-		}
-	}
-	asm volatile("cp.async.wait_group 0;");
+	using Scan = SgmScan<K, VEC, SD, PF>;
+	const int wib = threadIdx.x >> 5;
+	const int line = blockIdx.x * WPB + wib;
+	if (line >= (SD < 2 ? H : W)) return;          // whole warp
+	Scan sc;
+	sc.init(tab, in, out, sgm_smem + (size_t)wib * PF * 2 * Scan::VSZ + (threadIdx.x & 31) * K, H, W, D, pad, prm, line);
+	sc.run(0, SD < 2 ? W : H, !ZERO);
 }
 
-template <int K, bool VEC, int SD, bool ZERO>
+// Both horizontal directions of one image row in ONE CTA (two warps), for an accumulator that is
+// known to be zero on entry: warp 0 scans right, warp 1 scans left, concurrently (a horizontal
+// scan is 1226 strictly serial steps on only 370 lines, so a single direction leaves most SM
+// sub-partitions idle).  The reference's accumulation order out = (0 + right) + left is kept:
+// in the half of the row a scan reaches FIRST it stores 0 + v; after a block barrier at the
+// crossing point it adds its v to what the other scan stored.  For the left scan that is
+// (0 + right) + left literally; for the right scan it is (0 + right) + (0 + left), and
+// (0 + a) + b == (0 + b) + a holds in IEEE arithmetic (0 + a only canonicalises -0, + commutes).
+template <int K, bool VEC, int PF>
+__global__ void __launch_bounds__(64)
+sgm_hpair_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, float *__restrict__ out,
+		 int H, int W, int D, int pad, SgmParams prm)
+{
+	extern __shared__ __align__(16) float sgm_smem[];
+	const int line = blockIdx.x;
+	const int wib = threadIdx.x >> 5;
+	const int M = W / 2;                           // columns [0, M) are reached first by the right scan
+	float *ring = sgm_smem + (size_t)wib * PF * 2 * 32 * K + (threadIdx.x & 31) * K;
+	if (wib == 0) {
+		SgmScan<K, VEC, 0, PF> sc;
+		sc.init(tab, in, out, ring, H, W, D, pad, prm, line);
+		sc.run(0, M, false);
+		__syncthreads();
+		sc.run(M, W, true);
+	} else {
+		SgmScan<K, VEC, 1, PF> sc;
+		sc.init(tab, in, out, ring, H, W, D, pad, prm, line);
+		sc.run(0, W - M, false);                   // columns W-1 .. M
+		__syncthreads();
+		sc.run(W - M, W, true);                    // columns M-1 .. 0
+	}
+}
+
+static int sgm_pf_env()
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("ADCENSUS_SGM_PF"); v = e ? atoi(e) : 0; }
+	return v;
+}
+
+template <int K, bool VEC, int SD, bool ZERO, int PFX = 0>
 int launch_pass(const uint8_t *tab, const float *in, float *out, int H, int W, int D, int pad,
 		const SgmParams &prm, cudaStream_t s)
 {
-	constexpr int PF = K >= 16 ? 6 : 8;
+	if constexpr (PFX == 0 && SD < 2 && K == 8) {
+		if (sgm_pf_env() == 16) return launch_pass<K, VEC, SD, ZERO, 16>(tab, in, out, H, W, D, pad, prm, s);
+		if (sgm_pf_env() == 24) return launch_pass<K, VEC, SD, ZERO, 24>(tab, in, out, H, W, D, pad, prm, s);
+	}
+	constexpr int PF = PFX ? PFX : (K >= 16 ? 6 : 8);
 	// horizontal scans have few, long lines: one warp per CTA spreads them over all SMs
 	constexpr int WPB = SD < 2 ? 1 : 4;
-	constexpr int NR = 1;  // NR = 2 measured 2x slower: the two recurrences are not interleaved by ptxas
-	constexpr int NV = ZERO ? 1 : 2;
-	constexpr int SMEM = WPB * NR * PF * NV * 32 * K * 4;
-	auto kern = sgm_pass_kernel<K, VEC, SD, ZERO, PF, WPB, NR>;
+	constexpr int SMEM = WPB * PF * 2 * 32 * K * 4;
+	auto kern = sgm_pass_kernel<K, VEC, SD, ZERO, PF, WPB>;
 	if (SMEM > 48 * 1024) {
 		static bool done[64] = {false};
 		int dev = 0;
@@ -325,7 +463,32 @@ int launch_pass(const uint8_t *tab, const float *in, float *out, int H, int W, i
 		}
 	}
 	const int nlines = SD < 2 ? H : W;
-	kern<<<adc_div_up(nlines, WPB * NR), 32 * WPB, SMEM, s>>>(tab, in, out, H, W, D, pad, prm);
+	kern<<<adc_div_up(nlines, WPB), 32 * WPB, SMEM, s>>>(tab, in, out, H, W, D, pad, prm);
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+template <int K, bool VEC, int PFX = 0>
+int launch_hpair(const uint8_t *tab, const float *in, float *out, int H, int W, int D, int pad,
+		 const SgmParams &prm, cudaStream_t s)
+{
+	if constexpr (PFX == 0 && K == 8) {
+		if (sgm_pf_env() == 16) return launch_hpair<K, VEC, 16>(tab, in, out, H, W, D, pad, prm, s);
+		if (sgm_pf_env() == 24) return launch_hpair<K, VEC, 24>(tab, in, out, H, W, D, pad, prm, s);
+	}
+	constexpr int PF = PFX ? PFX : (K >= 16 ? 6 : 8);
+	constexpr int SMEM = 2 * PF * 2 * 32 * K * 4;
+	auto kern = sgm_hpair_kernel<K, VEC, PF>;
+	if (SMEM > 48 * 1024) {
+		static bool done[64] = {false};
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (!done[dev & 63]) {
+			ADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+			done[dev & 63] = true;
+		}
+	}
+	kern<<<H, 64, SMEM, s>>>(tab, in, out, H, W, D, pad, prm);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
@@ -336,11 +499,16 @@ int launch_all(const uint8_t *tab, const float *in, float *out, int H, int W, in
 	       const SgmParams &prm, bool zero_out, int pass_mask, cudaStream_t s)
 {
 	int rc = 0;
-	if (pass_mask & 1)
-		rc = zero_out ? launch_pass<K, VEC, 0, true>(tab, in, out, H, W, D, pad, prm, s)
-			      : launch_pass<K, VEC, 0, false>(tab, in, out, H, W, D, pad, prm, s);
+	if ((pass_mask & 3) == 3 && zero_out && W >= 2) {
+		rc = launch_hpair<K, VEC>(tab, in, out, H, W, D, pad, prm, s);   // right and left concurrently
+	} else {
+		if (pass_mask & 1)
+			rc = zero_out ? launch_pass<K, VEC, 0, true>(tab, in, out, H, W, D, pad, prm, s)
+				      : launch_pass<K, VEC, 0, false>(tab, in, out, H, W, D, pad, prm, s);
+		if (rc) return rc;
+		if ((pass_mask & 2) && (rc = launch_pass<K, VEC, 1, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
+	}
 	if (rc) return rc;
-	if ((pass_mask & 2) && (rc = launch_pass<K, VEC, 1, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
 	if ((pass_mask & 4) && (rc = launch_pass<K, VEC, 2, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
 	if (pass_mask & 8) rc = launch_pass<K, VEC, 3, false>(tab, in, out, H, W, D, pad, prm, s);
 	return rc;
