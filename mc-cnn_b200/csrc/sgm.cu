@@ -82,6 +82,27 @@ __global__ void sgm_class_kernel(const float *__restrict__ x0, const float *__re
 	tab[3 * plane + id] = v1;
 }
 
+// Vertical scans: per (table row ty, band column x, lane) one word that already holds the outcome of
+// the class comparisons of adcensus.cu:596-605 for the lane's K slots: bit k = (D2 class of slot k ==
+// D1 class), bits 16-17 = D1 class.  Every step of a vertical scan is a new table row, so this word
+// is the only class data a lane fetches per step (through the cp.async ring, like the costs).
+__host__ __device__ inline size_t sgm_sel_offset(int Ht, int Wp) { return ((size_t)4 * Ht * Wp + 16 + 255) & ~(size_t)255; }
+
+// block (32 lanes, 8 columns), grid (ceil(W / 8), Ht)
+__global__ void sgm_sel_kernel(const uint8_t *__restrict__ tab, unsigned *__restrict__ sel, int Ht, int W, int Wp, int pad,
+			       int xoff, int K, int ddir)
+{
+	const int lane = threadIdx.x, xb = blockIdx.x * 8 + threadIdx.y, ty = blockIdx.y;
+	if (xb >= W) return;
+	const long plane = (long)Ht * Wp;
+	const long col = (long)ty * Wp + pad + xoff + xb;
+	const unsigned c1 = __ldg(tab + plane + col);                // v0: D1 class (:587)
+	const uint8_t *q = tab + 3 * plane + col + (long)lane * K * ddir;   // v1: D2 classes (:588-594)
+	unsigned w = c1 << 16;
+	for (int k = 0; k < K; k++) w |= (unsigned)(__ldg(q + k * ddir) == c1) << k;
+	sel[((long)ty * W + xb) * 32 + lane] = w;
+}
+
 // ---------------------------------------------------------------- helpers
 __device__ __forceinline__ float warp_min_f32(float v)
 {
@@ -143,8 +164,34 @@ __device__ __forceinline__ void store_vec(const float (&r)[K], float *p, int dba
 }
 
 // ---------------------------------------------------------------- one scan direction
+// copy `nbytes` table bytes starting at `row` into shared memory with aligned word loads; returns
+// the shared-memory address of row[0].  Reads at most 3 bytes before / after the range (inside the
+// table, see adc_sgm_table_bytes).
+__device__ __forceinline__ const uint8_t *sgm_stage_row(unsigned *dst, const uint8_t *row, int nbytes, int tid, int nthreads)
+{
+	const uintptr_t a = (uintptr_t)row;
+	const unsigned *al = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
+	const int mis = (int)(a & 3);
+	const int nw = (mis + nbytes + 3) >> 2;
+	for (int i = tid; i < nw; i += nthreads) dst[i] = __ldg(al + i);
+	return reinterpret_cast<const uint8_t *>(dst) + mis;
+}
+
+__device__ __forceinline__ void cp_async4u(unsigned *smem_dst, const unsigned *gsrc)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
 
 // State of one warp scanning one line.  SD: 0 right, 1 left, 2 down, 3 up (adcensus.cu:541-565).
+//
+// Penalty classes (D1: one byte per step; D2: the bytes at K consecutive table columns per lane):
+//  horizontal scans: the CTA stages the two class rows of its image row in shared memory once; the
+//    K bytes of step s+1 are those of step s moved by one slot, so each lane keeps them in a
+//    register window that is shifted by one byte per step, with ONE byte read from shared memory;
+//  vertical scans: every step is a new table row; a lane fetches ONE pre-compared selector word
+//    (sgm_sel_kernel) per step through the same cp.async ring as the cost vectors, PF steps ahead.
+//    (Class bytes loaded one step ahead with plain loads were the top stall: they queue behind the
+//    streaming traffic and never hit L1.)
 template <int K, bool VEC, int SD, int PF>
 struct SgmScan {
 	static constexpr int VSZ = 32 * K;             // floats per cost vector slot (padded to 32*K)
@@ -152,38 +199,35 @@ struct SgmScan {
 	static constexpr int dy = SD == 2 ? 1 : (SD == 3 ? -1 : 0);
 	static constexpr int tshift_x = dx < 0 ? 1 : 0;
 	static constexpr int tshift_y = dy < 0 ? 1 : 0;
-	// How a lane gets the D2 classes of its K slots (bytes at consecutive table columns):
-	//  SLIDE  horizontal scans: the K bytes of step s+1 are those of step s moved by one slot, so a
-	//         register window is shifted and ONE new byte is loaded per step, three steps ahead;
-	//  WORDS  vertical scans: K new bytes per step, fetched one step ahead as K/4+1 aligned words
-	//         and funnel-shifted into place when consumed;
-	//  else   (K < 4) one byte load per slot, one step ahead.
-	// Nothing touches a loaded value in the step that issues the load (the table row changes every
-	// step of a vertical scan, so these loads miss L1; consumed just in time they were the top stall).
-	static constexpr bool SLIDE = SD < 2 && K % 4 == 0;
-	static constexpr bool WORDS = SD >= 2 && K % 4 == 0;
+	static constexpr bool HORIZ = SD < 2;
 	static constexpr int NWD = (K + 3) / 4;        // class window registers, 4 slots each
-	static constexpr int NRAW = K / 4 + 1;
+	static constexpr int CRING_WORDS = HORIZ ? 0 : PF * 32;   // selector ring, per warp
 
 	const float *in;
 	float *out;
 	float *ring;                                   // this lane's K floats of slot 0: [PF][2][VSZ] (in, out)
-	const uint8_t *t1, *t2;                        // D1 / D2 class planes, at image column xoff
-	int lane, dbase, D, Wp, Ht, W, yoff, ddir;
+	int lane, dbase, D, W, ddir;
 	long pix_step;
 	float P1f, P2f, P1s, P2s, P1m, P2m, P1f_a, P1s_a, P1m_a;
 	int x, y;                                      // pixel of the NEXT step to execute
 	long base;
 	float prev[K];
 	unsigned cw[NWD], c1c;                         // classes of the step being executed; byte k%4 of cw[k/4] = slot k
-	unsigned nw[NWD], q1, q2, c1q[3];              // SLIDE: next window, entering bytes, D1 classes ahead
-	const uint8_t *pe, *p1;
+	// horizontal
+	const uint8_t *p1, *pe;                        // shared-memory class rows: D1 of pixel xs at p1[xs], entering D2 byte at pe[xs]
+	unsigned nw[NWD], qn, c1n;                     // window / D1 class of the next step, byte entering the step after
 	int xl;
 	bool up;
-	unsigned raw[NRAW], cb[K], c1n;                // WORDS / byte path: classes of the next step
-	int rsh;
+	// vertical
+	unsigned *cring;                               // this lane's word of slot 0: [PF][32]
+	const unsigned *selp;                          // selector word of the next step to execute
+	long cstep;                                    // selector words per step (+-32*W)
+	unsigned selw;                                 // selector word of the step being executed
 
-	__device__ __forceinline__ void init(const uint8_t *tab, const float *in_, float *out_, float *ring_, int H, int W_, int D_,
+	// srow1 / srow2: (horizontal) shared-memory copies of the D1 / D2 class rows of this line, at
+	// image column 0 of the band.  cring_: (vertical) this warp's class ring.
+	__device__ __forceinline__ void init(const uint8_t *tab, const float *in_, float *out_, float *ring_, unsigned *cring_,
+					      const uint8_t *srow1, const uint8_t *srow2, int H, int W_, int D_,
 					      int pad, const SgmParams &prm, int line)
 	{
 		in = in_; out = out_; ring = ring_;
@@ -191,19 +235,12 @@ struct SgmScan {
 		dbase = lane * K;
 		D = D_;
 		W = W_;
+		ddir = prm.direction;
 		// adcensus.cu:595-605 and :609/:612, same expressions
 		P1f = prm.pi1; P2f = prm.pi2;
 		P1s = prm.pi1 / (prm.q1 * prm.q2); P2s = prm.pi2 / (prm.q1 * prm.q2);
 		P1m = prm.pi1 / prm.q1; P2m = prm.pi2 / prm.q1;
 		P1f_a = P1f / prm.alpha1; P1s_a = P1s / prm.alpha1; P1m_a = P1m / prm.alpha1;
-		// class tables: D1 from plane (SD<2 ? 0 : 1), D2 from plane (SD<2 ? 2 : 3).  The stored
-		// difference at (y, j) pairs pixel j with its left / upper neighbour, so scans that look
-		// right / down (dx = -1, dy = -1) read the entry one further.
-		Wp = prm.Wt + 2 * pad;
-		Ht = prm.Ht; yoff = prm.yoff; ddir = prm.direction;
-		const long plane = (long)prm.Ht * Wp;
-		t1 = tab + (SD < 2 ? 0 : 1) * plane + pad + prm.xoff;
-		t2 = tab + (SD < 2 ? 2 : 3) * plane + pad + prm.xoff;
 		x = SD == 0 ? 0 : (SD == 1 ? W - 1 : line);
 		y = SD == 2 ? 0 : (SD == 3 ? H - 1 : line);
 		pix_step = (long)(dy * W + dx) * D;
@@ -213,90 +250,59 @@ struct SgmScan {
 		for (int s = 0; s < PF * 2; s++)
 #pragma unroll
 			for (int k = 0; k < K; k++) ring[s * VSZ + k] = adc_nan();
-		cls_prime(x + dx, y + dy);                     // step 0 uses no penalties
-	}
-
-	__device__ __forceinline__ int clampx(int xs) const { return min(max(xs, 0), W - 1); }
-
-	// D1 class (:587) and D2 classes (:588-594) of pixel (xs, ys), the first recurrence step
-	__device__ __forceinline__ void cls_prime(int xs, int ys)
-	{
-		if constexpr (SLIDE) {
-			const int ty = min(max(ys + yoff, 0), Ht - 1);
-			const uint8_t *r2 = t2 + (long)ty * Wp + tshift_x;
-			p1 = t1 + (long)ty * Wp + tshift_x;
+		// The stored difference at (y, j) pairs pixel j with its left / upper neighbour, so scans
+		// that look right / down (dx = -1, dy = -1) read the entry one further (tshift).
+		if constexpr (HORIZ) {
+			// step 0 uses no penalties; prepare step 1 = pixel x + dx
+			const int xs = clampx(x + dx);
+			p1 = srow1 + tshift_x;
+			const uint8_t *r2 = srow2 + tshift_x;
 			up = dx * ddir < 0;                        // slot k of the next step = slot k-1 of this one
 			pe = r2 + (dbase + (up ? 0 : K - 1)) * ddir;
 #pragma unroll
 			for (int i = 0; i < NWD; i++) nw[i] = 0;
 #pragma unroll
-			for (int k = 0; k < K; k++)
-				nw[k / 4] |= (unsigned)__ldg(r2 + clampx(xs) + (dbase + k) * ddir) << (8 * (k & 3));
-			c1q[0] = __ldg(p1 + clampx(xs));
-			c1q[1] = __ldg(p1 + clampx(xs + dx));
-			c1q[2] = __ldg(p1 + clampx(xs + 2 * dx));
-			q1 = __ldg(pe + clampx(xs + dx));
-			q2 = __ldg(pe + clampx(xs + 2 * dx));
-			xl = xs + 3 * dx;
+			for (int k = 0; k < K; k++) nw[k / 4] |= (unsigned)r2[xs + (dbase + k) * ddir] << (8 * (k & 3));   // :588-594
+			c1n = p1[xs];                              // :587
+			qn = pe[clampx(xs + dx)];
+			xl = xs + dx;
 		} else {
-			cls_fetch(xs, ys);
+			const int Wp = prm.Wt + 2 * pad;
+			cring = cring_;
+			cstep = (long)dy * W * 32;
+			selp = reinterpret_cast<const unsigned *>(tab + sgm_sel_offset(prm.Ht, Wp)) +
+			       ((long)(y + prm.yoff + tshift_y) * W + x) * 32 + lane;       // step 0 (never fetched)
 		}
 	}
 
-	__device__ __forceinline__ void cls_fetch(int xs, int ys)
-	{
-		const int ty = min(max(ys + yoff + tshift_y, 0), Ht - 1);           // image row of the stored difference
-		const uint8_t *q = t2 + (long)ty * Wp + xs + tshift_x + dbase * ddir;
-		c1n = __ldg(t1 + (long)ty * Wp + xs + tshift_x);
-		if constexpr (WORDS) {
-			const uintptr_t lo = (uintptr_t)(ddir > 0 ? q : q - (K - 1));   // lowest address of the K bytes
-			rsh = (int)(lo & 3) * 8;
-			const unsigned *al = reinterpret_cast<const unsigned *>(lo & ~(uintptr_t)3);
-#pragma unroll
-			for (int i = 0; i < NRAW; i++) raw[i] = __ldg(al + i);
-		} else {
-#pragma unroll
-			for (int k = 0; k < K; k++) cb[k] = __ldg(q + k * ddir);
-		}
-	}
+	__device__ __forceinline__ int clampx(int xs) const { return min(max(xs, 0), W - 1); }
 
-	// classes of the step about to execute -> (c1c, cw); start the loads for later steps
-	__device__ __forceinline__ void cls_take()
+	// vertical: start the copy of the selector word of the step `ahead` steps after the next one
+	__device__ __forceinline__ void cls_issue(int slot, int ahead) { cp_async4u(cring + slot * 32, selp + ahead * cstep); }
+
+	// classes of the step about to execute -> (c1c, cw)
+	__device__ __forceinline__ void cls_take(int slot)
 	{
-		if constexpr (SLIDE) {
+		if constexpr (HORIZ) {
 #pragma unroll
 			for (int i = 0; i < NWD; i++) cw[i] = nw[i];
-			c1c = c1q[0];
+			c1c = c1n;
+			constexpr unsigned topmask = (1u << (8 * ((K - 1) & 3))) - 1u;   // bytes below the top slot of the last word
 			if (up) {
 #pragma unroll
 				for (int i = NWD - 1; i > 0; i--) nw[i] = __funnelshift_l(nw[i - 1], nw[i], 8);
-				nw[0] = (nw[0] << 8) | q1;
+				nw[0] = (nw[0] << 8) | qn;
 			} else {
 #pragma unroll
 				for (int i = 0; i < NWD - 1; i++) nw[i] = __funnelshift_r(nw[i], nw[i + 1], 8);
-				nw[NWD - 1] = (nw[NWD - 1] >> 8) | (q1 << 24);
+				nw[NWD - 1] = ((nw[NWD - 1] >> 8) & topmask) | (qn << (8 * ((K - 1) & 3)));
 			}
-			q1 = q2;
-			c1q[0] = c1q[1];
-			c1q[1] = c1q[2];
-			const int xc = clampx(xl);
-			q2 = __ldg(pe + xc);
-			c1q[2] = __ldg(p1 + xc);
+			c1n = p1[clampx(xl)];
+			qn = pe[clampx(xl + dx)];
 			xl += dx;
 		} else {
-			c1c = c1n;
-			if constexpr (WORDS) {
-				unsigned w[K / 4];
-#pragma unroll
-				for (int i = 0; i < K / 4; i++) w[i] = __funnelshift_r(raw[i], raw[i + 1], rsh);
-#pragma unroll
-				for (int i = 0; i < K / 4; i++) cw[i] = ddir > 0 ? w[i] : __byte_perm(w[K / 4 - 1 - i], 0, 0x0123);
-			} else {
-				cw[0] = 0;
-#pragma unroll
-				for (int k = 0; k < K; k++) cw[0] |= cb[k] << (8 * k);
-			}
-			cls_fetch(x + dx, y + dy);                 // for the step after this one
+			selw = cring[slot * 32];
+			c1c = (selw >> 16) & 3u;
 		}
 	}
 
@@ -310,6 +316,8 @@ struct SgmScan {
 			if (s_begin + u < s_end) {
 				issue_vec<K, VEC>(ring + (u * 2) * VSZ, in + base + u * pix_step, dbase, D);
 				if (use_out) issue_vec<K, VEC>(ring + (u * 2 + 1) * VSZ, out + base + u * pix_step, dbase, D);
+				if constexpr (!HORIZ)
+					if (s_begin + u >= 1) cls_issue(u, u);
 			}
 			asm volatile("cp.async.commit_group;");
 		}
@@ -317,6 +325,7 @@ struct SgmScan {
 #pragma unroll 1
 		for (int s = s_begin; s < s_end; s++) {
 			float *rs = ring + slot * (2 * VSZ);
+			const int cslot = slot;
 			slot = slot + 1 == PF ? 0 : slot + 1;
 			asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1));
 			float cin[K], cout[K];
@@ -341,7 +350,7 @@ struct SgmScan {
 				if (lane == 0) left = adc_nan();                // d - 1 < 0 (:608)
 				if (lane == 31) right = adc_nan();
 
-				cls_take();
+				cls_take(cslot);
 				// penalties when the D2 class equals the D1 class (both < tau or both > tau), else middle
 				const unsigned c1 = c1c;
 				const bool c1lt = c1 == 0;
@@ -350,10 +359,10 @@ struct SgmScan {
 				const float P1ae = c1 == 1 ? P1m_a : (c1lt ? P1f_a : P1s_a);
 				unsigned xw[NWD];
 #pragma unroll
-				for (int i = 0; i < NWD; i++) xw[i] = cw[i] ^ (c1 * 0x01010101u);
+				for (int i = 0; i < NWD; i++) xw[i] = HORIZ ? cw[i] ^ (c1 * 0x01010101u) : 0u;
 #pragma unroll
 				for (int k = 0; k < K; k++) {
-					const bool eq = (xw[k / 4] & (0xffu << (8 * (k & 3)))) == 0;
+					const bool eq = HORIZ ? (xw[k / 4] & (0xffu << (8 * (k & 3)))) == 0 : (selw >> k) & 1u;
 					const float P1 = eq ? P1e : P1m, P2 = eq ? P2e : P2m, P1a = eq ? P1ae : P1m_a;
 					const float pm = k > 0 ? prev[k - 1] : left;
 					const float pp = k < K - 1 ? prev[k + 1] : right;
@@ -374,15 +383,22 @@ struct SgmScan {
 			if (s + PF < s_end) {
 				issue_vec<K, VEC>(rs, in + base + PF * pix_step, dbase, D);
 				if (use_out) issue_vec<K, VEC>(rs + VSZ, out + base + PF * pix_step, dbase, D);
+				if constexpr (!HORIZ) cls_issue(cslot, PF);
 			}
 			asm volatile("cp.async.commit_group;");
 			base += pix_step;
 			x += dx;
 			y += dy;
+			if constexpr (!HORIZ) {
+				selp += cstep;
+			}
 		}
 		asm volatile("cp.async.wait_group 0;");
 	}
 };
+
+// shared-memory bytes of one staged class row (horizontal scans)
+__host__ __device__ inline int sgm_row_bytes(int Wt, int pad) { return (Wt + 2 * pad + 8 + 15) & ~15; }
 
 // One launch = one direction: one warp per scanline.  ZERO: output known to be 0 on entry.
 template <int K, bool VEC, int SD, bool ZERO, int PF, int WPB>
@@ -393,10 +409,26 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 	extern __shared__ __align__(16) float sgm_smem[];
 	using Scan = SgmScan<K, VEC, SD, PF>;
 	const int wib = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
 	const int line = blockIdx.x * WPB + wib;
 	if (line >= (SD < 2 ? H : W)) return;          // whole warp
+	float *ring = sgm_smem + (size_t)wib * PF * 2 * Scan::VSZ;
+	unsigned *extra = reinterpret_cast<unsigned *>(sgm_smem + (size_t)WPB * PF * 2 * Scan::VSZ);
+	const uint8_t *s1 = nullptr, *s2 = nullptr;
+	unsigned *cring = nullptr;
+	if constexpr (SD < 2) {
+		const int Wp = prm.Wt + 2 * pad, RB = sgm_row_bytes(prm.Wt, pad);
+		const long plane = (long)prm.Ht * Wp;
+		const int ty = min(max(line + prm.yoff, 0), prm.Ht - 1);
+		unsigned *rows = extra + (size_t)wib * (2 * RB / 4);
+		s1 = sgm_stage_row(rows, tab + (long)ty * Wp, Wp, lane, 32) + pad + prm.xoff;                      // plane 0
+		s2 = sgm_stage_row(rows + RB / 4, tab + 2 * plane + (long)ty * Wp, Wp, lane, 32) + pad + prm.xoff;   // plane 2
+		__syncwarp();
+	} else {
+		cring = extra + (size_t)wib * Scan::CRING_WORDS + lane;
+	}
 	Scan sc;
-	sc.init(tab, in, out, sgm_smem + (size_t)wib * PF * 2 * Scan::VSZ + (threadIdx.x & 31) * K, H, W, D, pad, prm, line);
+	sc.init(tab, in, out, ring + lane * K, cring, s1, s2, H, W, D, pad, prm, line);
 	sc.run(0, SD < 2 ? W : H, !ZERO);
 }
 
@@ -418,77 +450,75 @@ sgm_hpair_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, 
 	const int wib = threadIdx.x >> 5;
 	const int M = W / 2;                           // columns [0, M) are reached first by the right scan
 	float *ring = sgm_smem + (size_t)wib * PF * 2 * 32 * K + (threadIdx.x & 31) * K;
+	// the two scans share the class rows of the line
+	const int Wp = prm.Wt + 2 * pad, RB = sgm_row_bytes(prm.Wt, pad);
+	const long plane = (long)prm.Ht * Wp;
+	const int ty = min(max(line + prm.yoff, 0), prm.Ht - 1);
+	unsigned *rows = reinterpret_cast<unsigned *>(sgm_smem + (size_t)2 * PF * 2 * 32 * K);
+	const uint8_t *s1 = sgm_stage_row(rows, tab + (long)ty * Wp, Wp, threadIdx.x, 64) + pad + prm.xoff;
+	const uint8_t *s2 = sgm_stage_row(rows + RB / 4, tab + 2 * plane + (long)ty * Wp, Wp, threadIdx.x, 64) + pad + prm.xoff;
+	__syncthreads();
 	if (wib == 0) {
 		SgmScan<K, VEC, 0, PF> sc;
-		sc.init(tab, in, out, ring, H, W, D, pad, prm, line);
+		sc.init(tab, in, out, ring, nullptr, s1, s2, H, W, D, pad, prm, line);
 		sc.run(0, M, false);
 		__syncthreads();
 		sc.run(M, W, true);
 	} else {
 		SgmScan<K, VEC, 1, PF> sc;
-		sc.init(tab, in, out, ring, H, W, D, pad, prm, line);
+		sc.init(tab, in, out, ring, nullptr, s1, s2, H, W, D, pad, prm, line);
 		sc.run(0, W - M, false);                   // columns W-1 .. M
 		__syncthreads();
 		sc.run(W - M, W, true);                    // columns M-1 .. 0
 	}
 }
 
-static int sgm_pf_env()
+constexpr int SGM_SMEM_MAX = 160 * 1024;
+
+// done: one flag array per kernel instantiation (the caller's static)
+template <typename Kern>
+int sgm_allow_smem(Kern kern, int smem, bool *done)
 {
-	static int v = -1;
-	if (v < 0) { const char *e = getenv("ADCENSUS_SGM_PF"); v = e ? atoi(e) : 0; }
-	return v;
+	if (smem > SGM_SMEM_MAX) return ADCENSUS_ELIMIT;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!done[dev & 63]) {
+		ADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SGM_SMEM_MAX));
+		done[dev & 63] = true;
+	}
+	return 0;
 }
 
-template <int K, bool VEC, int SD, bool ZERO, int PFX = 0>
+template <int K, bool VEC, int SD, bool ZERO>
 int launch_pass(const uint8_t *tab, const float *in, float *out, int H, int W, int D, int pad,
 		const SgmParams &prm, cudaStream_t s)
 {
-	if constexpr (PFX == 0 && SD < 2 && K == 8) {
-		if (sgm_pf_env() == 16) return launch_pass<K, VEC, SD, ZERO, 16>(tab, in, out, H, W, D, pad, prm, s);
-		if (sgm_pf_env() == 24) return launch_pass<K, VEC, SD, ZERO, 24>(tab, in, out, H, W, D, pad, prm, s);
-	}
-	constexpr int PF = PFX ? PFX : (K >= 16 ? 6 : 8);
+	constexpr int PF = K >= 16 ? 6 : 8;
 	// horizontal scans have few, long lines: one warp per CTA spreads them over all SMs
 	constexpr int WPB = SD < 2 ? 1 : 4;
-	constexpr int SMEM = WPB * PF * 2 * 32 * K * 4;
+	using Scan = SgmScan<K, VEC, SD, PF>;
+	const int smem = WPB * (PF * 2 * Scan::VSZ * 4 + Scan::CRING_WORDS * 4 + (SD < 2 ? 2 * sgm_row_bytes(prm.Wt, pad) : 0));
 	auto kern = sgm_pass_kernel<K, VEC, SD, ZERO, PF, WPB>;
-	if (SMEM > 48 * 1024) {
-		static bool done[64] = {false};
-		int dev = 0;
-		cudaGetDevice(&dev);
-		if (!done[dev & 63]) {
-			ADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-			done[dev & 63] = true;
-		}
-	}
+	static bool done[64] = {false};
+	int rc = sgm_allow_smem(kern, smem, done);
+	if (rc) return rc;
 	const int nlines = SD < 2 ? H : W;
-	kern<<<adc_div_up(nlines, WPB), 32 * WPB, SMEM, s>>>(tab, in, out, H, W, D, pad, prm);
+	kern<<<adc_div_up(nlines, WPB), 32 * WPB, smem, s>>>(tab, in, out, H, W, D, pad, prm);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
 
-template <int K, bool VEC, int PFX = 0>
+template <int K, bool VEC>
 int launch_hpair(const uint8_t *tab, const float *in, float *out, int H, int W, int D, int pad,
 		 const SgmParams &prm, cudaStream_t s)
 {
-	if constexpr (PFX == 0 && K == 8) {
-		if (sgm_pf_env() == 16) return launch_hpair<K, VEC, 16>(tab, in, out, H, W, D, pad, prm, s);
-		if (sgm_pf_env() == 24) return launch_hpair<K, VEC, 24>(tab, in, out, H, W, D, pad, prm, s);
-	}
-	constexpr int PF = PFX ? PFX : (K >= 16 ? 6 : 8);
-	constexpr int SMEM = 2 * PF * 2 * 32 * K * 4;
+	constexpr int PF = K >= 16 ? 6 : 8;
+	const int smem = 2 * PF * 2 * 32 * K * 4 + 2 * sgm_row_bytes(prm.Wt, pad);
 	auto kern = sgm_hpair_kernel<K, VEC, PF>;
-	if (SMEM > 48 * 1024) {
-		static bool done[64] = {false};
-		int dev = 0;
-		cudaGetDevice(&dev);
-		if (!done[dev & 63]) {
-			ADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-			done[dev & 63] = true;
-		}
-	}
-	kern<<<H, 64, SMEM, s>>>(tab, in, out, H, W, D, pad, prm);
+	static bool done[64] = {false};
+	int rc = sgm_allow_smem(kern, smem, done);
+	if (rc) return rc;
+	kern<<<H, 64, smem, s>>>(tab, in, out, H, W, D, pad, prm);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
@@ -520,7 +550,8 @@ int launch_all(const uint8_t *tab, const float *in, float *out, int H, int W, in
 // that the padding slots d >= D also index inside the row
 static int sgm_slots(int D) { return D <= 32 ? 32 : (D <= 64 ? 64 : (D <= 128 ? 128 : (D <= 256 ? 256 : 512))); }
 
-size_t adc_sgm_table_bytes(int H, int W, int D) { return 4 * (size_t)H * (W + 2 * (size_t)sgm_slots(D)) + 16; }
+// four byte-class planes + the selector words of the vertical scans (128 bytes per pixel)
+size_t adc_sgm_table_bytes(int H, int W, int D) { return sgm_sel_offset(H, W + 2 * sgm_slots(D)) + (size_t)128 * H * W; }
 
 int adc_sgm_classes(const float *x0, const float *x1, uint8_t *tab, int Ht, int Wt, int D, float tau_so, cudaStream_t s)
 {
@@ -540,6 +571,11 @@ int adc_sgm2_band(const float *in, float *out, const uint8_t *tab, int H, int W,
 {
 	SgmParams prm{pi1, pi2, tau_so, alpha1, q1, q2, direction, Ht, Wt, yoff, xoff};
 	const int pad = sgm_slots(D);
+	if (pass_mask & 12) {                              // vertical scans: band = whole columns (H == Ht)
+		unsigned *sel = reinterpret_cast<unsigned *>(const_cast<uint8_t *>(tab) + sgm_sel_offset(Ht, Wt + 2 * pad));
+		sgm_sel_kernel<<<dim3(adc_div_up(W, 8), Ht), dim3(32, 8), 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, pad / 32, direction);
+		ADC_CHECK_LAUNCH();
+	}
 	const bool vec = (D % 4 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0);
 	if (D <= 32) return launch_all<1, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
 	if (D <= 64) return launch_all<2, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
