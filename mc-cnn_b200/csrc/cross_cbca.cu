@@ -74,6 +74,24 @@ __global__ void pack_arms_kernel(const float *__restrict__ xc, uint32_t *__restr
 	if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxlen, m);
 }
 
+// packed fp32 pairs for FFMA2 (sm_100a): two independent round-to-nearest fmas per instruction
+__device__ __forceinline__ unsigned long long adc_pack2(float lo, float hi)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void adc_unpack2(unsigned long long v, float &lo, float &hi)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long adc_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+	unsigned long long d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+
 // ------------------------------------------------------------------ cbca, fixed-window column strips
 // (arms up to 5 pixels: every KITTI preset, main.lua:86-113,207-262)
 //
@@ -236,16 +254,20 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 			__syncthreads();
 		}
 
+		// Outputs are accumulated in PAIRS (rows 2j, 2j+1) with the packed FFMA2 of sm_100a
+		// (fma.rn.f32x2: two independent IEEE fmas per instruction): {acc[2j], acc[2j+1]} +=
+		// {q[2j], q[2j+1]} * wm[k].  A row touches 2R+1 outputs = R+1 pairs, so a slot costs R+1
+		// instructions instead of 2R+1; the pair member outside the range gets q = 0 (acc unchanged).
 		int U[CW_NVT], Dn[CW_NVT];
-		float acc[CW_NVT], cnt[CW_NVT];
+		unsigned long long acc2[CW_NVT / 2], cnt2[CW_NVT / 2];
 #pragma unroll
 		for (int oy = 0; oy < CW_NVT; oy++) {
 			const uint32_t c = scomb[(ry + oy + R) * CW_TX + cx];
 			U[oy] = (c >> 16) & 255;
 			Dn[oy] = c >> 24;
-			acc[oy] = 0.0f;
-			cnt[oy] = 0.0f;
 		}
+#pragma unroll
+		for (int j = 0; j < CW_NVT / 2; j++) acc2[j] = cnt2[j] = adc_pack2(0.0f, 0.0f);
 
 #pragma unroll
 		for (int ri = 0; ri < CW_NVT + 2 * R; ri++) {
@@ -253,40 +275,50 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 			const uint32_t c = scomb[(ry + ri) * CW_TX + cx];
 			const int L = c & 255, Rr = (c >> 8) & 255;
 			const float LRf = (float)(L + Rr - 1);             // taps of this row's run (:364-369), exact in fp32
-			float wm[2 * R + 1];
-			float S = 0.0f;
+			const unsigned long long LR2 = adc_pack2(LRf, LRf);
+			unsigned long long wm2[2 * R + 1];
+			unsigned long long S2 = 0;
 			if constexpr (FAST) {
 				// sum of the run (x - L, x + Rr): tile columns [cx + R - L + 1, cx + R + Rr)
 				const float *prow = sp + (ry + ri) * PW + cx + R;
-				S = prow[Rr] - prow[1 - L];
+				const float S = prow[Rr] - prow[1 - L];
+				S2 = adc_pack2(S, S);
 			} else {
 #pragma unroll
 				for (int k = 0; k <= 2 * R; k++) {
 					// slot inside the run (x - L, x + Rr) (:362-364) keeps its value, the others become +0.0f
 					const float v = wrow[k];
-					wm[k] = k < R ? (L > R - k ? v : 0.0f) : (k > R ? (Rr > k - R ? v : 0.0f) : (L > 0 ? v : 0.0f));
+					const float w = k < R ? (L > R - k ? v : 0.0f) : (k > R ? (Rr > k - R ? v : 0.0f) : (L > 0 ? v : 0.0f));
+					wm2[k] = adc_pack2(w, w);
 				}
 			}
 #pragma unroll
-			for (int oy = 0; oy < CW_NVT; oy++) {
-				const int delta = ri - oy - R;                 // row offset from this output's centre row
-				if (delta < -R || delta > R) continue;
-				// 1.0f for a row inside this output's vertical arm (:361); the centre row iff the output is valid
-				const float qf = (delta < 0 ? U[oy] > -delta : Dn[oy] > delta) ? 1.0f : 0.0f;
+			for (int j = 0; j < CW_NVT / 2; j++) {
+				// row offset from the centre rows of outputs 2j and 2j+1
+				const int dlo = ri - 2 * j - R, dhi = dlo - 1;
+				const bool inlo = dlo >= -R && dlo <= R, inhi = dhi >= -R && dhi <= R;
+				if (!inlo && !inhi) continue;
+				// 1.0f for a row inside the output's vertical arm (:361); the centre row iff the output is valid
+				const float qlo = inlo && (dlo < 0 ? U[2 * j] > -dlo : Dn[2 * j] > dlo) ? 1.0f : 0.0f;
+				const float qhi = inhi && (dhi < 0 ? U[2 * j + 1] > -dhi : Dn[2 * j + 1] > dhi) ? 1.0f : 0.0f;
+				const unsigned long long q2 = adc_pack2(qlo, qhi);
 				if constexpr (FAST) {
-					acc[oy] = fmaf(S, qf, acc[oy]);
+					acc2[j] = adc_fma2(q2, S2, acc2[j]);
 				} else {
 #pragma unroll
-					for (int k = 0; k <= 2 * R; k++) acc[oy] = fmaf(wm[k], qf, acc[oy]);   // :364-367
+					for (int k = 0; k <= 2 * R; k++) acc2[j] = adc_fma2(q2, wm2[k], acc2[j]);   // :364-367
 				}
-				cnt[oy] = fmaf(LRf, qf, cnt[oy]);                                          // :368
+				cnt2[j] = adc_fma2(q2, LR2, cnt2[j]);                                          // :368
 			}
 		}
 #pragma unroll
 		for (int oy = 0; oy < CW_NVT; oy++) {
 			const int y = y0 + ry + oy;
 			if (y >= H || x >= W) continue;
-			float res = valid_col ? acc[oy] / cnt[oy]                                      // :373
+			float alo, ahi, clo, chi;
+			adc_unpack2(acc2[oy / 2], alo, ahi);
+			adc_unpack2(cnt2[oy / 2], clo, chi);
+			float res = valid_col ? ((oy & 1) ? ahi / chi : alo / clo)                     // :373
 					      : sv[(ry + oy + R) * TWP + cx + R];                      // :353-354 (keeps NaN)
 			out[(long)d * HW + (long)y * W + x] = res;
 		}
