@@ -88,19 +88,38 @@ __global__ void sgm_class_kernel(const float *__restrict__ x0, const float *__re
 // is the only class data a lane fetches per step (through the cp.async ring, like the costs).
 __host__ __device__ inline size_t sgm_sel_offset(int Ht, int Wp) { return ((size_t)4 * Ht * Wp + 16 + 255) & ~(size_t)255; }
 
-// block (32 lanes, 8 columns), grid (ceil(W / 8), Ht)
+// block (32 lanes, 8 columns), grid (ceil(W / 8), Ht).  K % 4 == 0: the lane's K class bytes are read as
+// K/4+1 aligned words and compared four at a time (classes are 0..2, so a byte of the xor with the D1
+// class is zero iff neither of its two low bits is set).
+template <int K>
 __global__ void sgm_sel_kernel(const uint8_t *__restrict__ tab, unsigned *__restrict__ sel, int Ht, int W, int Wp, int pad,
-			       int xoff, int K, int ddir)
+			       int xoff, int ddir)
 {
 	const int lane = threadIdx.x, xb = blockIdx.x * 8 + threadIdx.y, ty = blockIdx.y;
 	if (xb >= W) return;
 	const long plane = (long)Ht * Wp;
 	const long col = (long)ty * Wp + pad + xoff + xb;
 	const unsigned c1 = __ldg(tab + plane + col);                // v0: D1 class (:587)
-	const uint8_t *q = tab + 3 * plane + col + (long)lane * K * ddir;   // v1: D2 classes (:588-594)
-	unsigned w = c1 << 16;
-	for (int k = 0; k < K; k++) w |= (unsigned)(__ldg(q + k * ddir) == c1) << k;
-	sel[((long)ty * W + xb) * 32 + lane] = w;
+	const uint8_t *q = tab + 3 * plane + col + (long)lane * K * ddir;   // v1: D2 classes (:588-594), slot k at q[k * ddir]
+	unsigned w = 0;
+	if constexpr (K % 4 == 0) {
+		const uintptr_t lo = (uintptr_t)(ddir > 0 ? q : q - (K - 1));
+		const unsigned *al = reinterpret_cast<const unsigned *>(lo & ~(uintptr_t)3);
+		const int sh = (int)(lo & 3) * 8;
+		unsigned raw[K / 4 + 1];
+#pragma unroll
+		for (int i = 0; i <= K / 4; i++) raw[i] = __ldg(al + i);
+#pragma unroll
+		for (int i = 0; i < K / 4; i++) {
+			const unsigned x = __funnelshift_r(raw[i], raw[i + 1], sh) ^ (c1 * 0x01010101u);
+			const unsigned e = ~(x | (x >> 1)) & 0x01010101u;    // bit 8b set iff byte b equals c1
+			w |= ((e * 0x00204081u) >> 21 & 0xfu) << (4 * i);      // gather bits 0, 8, 16, 24 -> 0..3 (ascending address)
+		}
+		if (ddir < 0) w = __brev(w) >> (32 - K);                 // slot k sits at the k-th address from the top
+	} else {
+		for (int k = 0; k < K; k++) w |= (unsigned)(__ldg(q + k * ddir) == c1) << k;
+	}
+	sel[((long)ty * W + xb) * 32 + lane] = w | (c1 << 16);
 }
 
 // ---------------------------------------------------------------- helpers
@@ -573,7 +592,14 @@ int adc_sgm2_band(const float *in, float *out, const uint8_t *tab, int H, int W,
 	const int pad = sgm_slots(D);
 	if (pass_mask & 12) {                              // vertical scans: band = whole columns (H == Ht)
 		unsigned *sel = reinterpret_cast<unsigned *>(const_cast<uint8_t *>(tab) + sgm_sel_offset(Ht, Wt + 2 * pad));
-		sgm_sel_kernel<<<dim3(adc_div_up(W, 8), Ht), dim3(32, 8), 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, pad / 32, direction);
+		const dim3 grid(adc_div_up(W, 8), Ht), block(32, 8);
+		switch (pad / 32) {
+		case 1: sgm_sel_kernel<1><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
+		case 2: sgm_sel_kernel<2><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
+		case 4: sgm_sel_kernel<4><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
+		case 8: sgm_sel_kernel<8><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
+		default: sgm_sel_kernel<16><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
+		}
 		ADC_CHECK_LAUNCH();
 	}
 	const bool vec = (D % 4 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0);

@@ -33,6 +33,23 @@ constexpr int SJ_CCH = 8;       // channels per pipeline stage
 constexpr int SJ_NSTAGE = 3;
 constexpr int SJ_ROW = SJ_TX + 2 * SJ_TX;   // floats per channel row: [L 128][R 256]
 
+__device__ __forceinline__ unsigned long long sj_pack2(float lo, float hi)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void sj_unpack2(unsigned long long v, float &lo, float &hi)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sj_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+	unsigned long long d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+
 template <int NS>
 struct SJCfg {
 	static constexpr int DC = 16 * NS - 8;          // disparities per CTA
@@ -98,11 +115,13 @@ stereo_join_kernel(const float *__restrict__ gL, const float *__restrict__ gR,
 		}
 	};
 
-	float acc[8][16];
+	// accumulators as packed pairs (ji = 2m, 2m+1) for FFMA2 (fma.rn.f32x2: two independent IEEE
+	// fmas per instruction, the pair of R values times one broadcast -L value)
+	unsigned long long acc2[8][8];
 #pragma unroll
 	for (int i = 0; i < 8; i++)
 #pragma unroll
-		for (int j = 0; j < 16; j++) acc[i][j] = 0.0f;
+		for (int j = 0; j < 8; j++) acc2[i][j] = sj_pack2(0.0f, 0.0f);
 
 	// this tile's disparities: d - d0 = DC-1 - 16 s + xi - ji
 	const int dtop = d0 + (DC - 1) - 16 * s;             // d at (xi - ji) = 0
@@ -133,16 +152,25 @@ stereo_join_kernel(const float *__restrict__ gL, const float *__restrict__ gR,
 				*reinterpret_cast<float4 *>(&r[4]) = *reinterpret_cast<const float4 *>(row + 128 + rofs);
 				*reinterpret_cast<float4 *>(&r[8]) = *reinterpret_cast<const float4 *>(row + rofs + 4);
 				*reinterpret_cast<float4 *>(&r[12]) = *reinterpret_cast<const float4 *>(row + 128 + rofs + 4);
+				unsigned long long r2[8];
 #pragma unroll
-				for (int xi = 0; xi < 8; xi++)
+				for (int m = 0; m < 8; m++) r2[m] = sj_pack2(r[2 * m], r[2 * m + 1]);
 #pragma unroll
-					for (int ji = 0; ji < 16; ji++)
-						acc[xi][ji] = fmaf(-l[xi], r[ji], acc[xi][ji]);  // adcensus.cu:1470
+				for (int xi = 0; xi < 8; xi++) {
+					const unsigned long long nl = sj_pack2(-l[xi], -l[xi]);
+#pragma unroll
+					for (int m = 0; m < 8; m++) acc2[xi][m] = sj_fma2(r2[m], nl, acc2[xi][m]);  // adcensus.cu:1470: sum -= l * r
+				}
 			}
 		}
 	}
 	asm volatile("cp.async.wait_group 0;");
 	__syncthreads();                                     // pipeline buffers are reused as the output stage
+	float acc[8][16];
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+#pragma unroll
+		for (int m = 0; m < 8; m++) sj_unpack2(acc2[i][m], acc[i][2 * m], acc[i][2 * m + 1]);
 
 	// ---- epilogue 1: tile diagonals (fixed d, consecutive x) -> so[dd][split(x)] -------------
 	float *so = smem;
