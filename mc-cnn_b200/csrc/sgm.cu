@@ -15,9 +15,13 @@
 //     warp in flight and hides HBM latency behind the serial recurrence;
 //   * the P1/P2 selection (adcensus.cu:586-605) is table driven: a pre-pass
 //     classifies |I(p) - I(p-r)| against tau_so once per image / scan axis into
-//     byte tables (padded by D columns of the out-of-image class, D2 = 10), so a
-//     step needs one byte per disparity instead of two image loads and two
-//     bounds checks.
+//     byte tables (padded by D columns of the out-of-image class, D2 = 10).
+//     Horizontal scans stage the two class rows of their image row in shared
+//     memory and slide a register window of class bytes by one byte per step;
+//     vertical scans fetch one pre-compared selector word per lane and step
+//     (sgm_sel_kernel) through the cp.async ring;
+//   * the two horizontal directions of a row run in ONE CTA (sgm_hpair_kernel)
+//     when the accumulator is known to be zero, meeting at the row's midpoint.
 //
 // Arithmetic is the reference's, expression for expression (adds, fminf, IEEE
 // divisions; nothing contractible), and `out` is accumulated in the reference's

@@ -122,6 +122,33 @@ def test_sgm2(oracle, H, W, D, direction):
     same(out2, want2, "sgm2 accumulate")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,D,direction", [(11, 37, 20, -1), (10, 45, 70, 1), (7, 300, 228, -1)])
+def test_sgm2_bands_equal_whole_image(oracle, H, W, D, direction):
+    """mccnn_sgm2_band: horizontal passes on row bands (known-zero accumulator: both directions in one CTA),
+    then vertical passes on column bands, must reproduce the whole-image sgm2 bit for bit (the single-GPU
+    form of what rowband.py does across GPUs)."""
+    from mccnn_b200 import rowband
+
+    p = synth.make_pair(H, W, 4, D, seed=3 * D)
+    volL, volR = oracle.stereo_join(p["featL"], p["featR"], D)
+    vol = oracle.transpose_dhw_to_hwd(volL if direction == -1 else volR)
+    opt = pipeline.make_params("kitti", "fast")
+    want = oracle.sgm2(p["imgL"], p["imgR"], vol, opt.pi1, opt.pi2, opt.tau_so, opt.alpha1, opt.sgm_q1, opt.sgm_q2, direction)
+    ops = rowband.CudaOps()
+    iL, iR, cost = cu(p["imgL"]), cu(p["imgR"]), cu(vol)
+    acc = torch.zeros_like(cost)
+    for y0, y1 in ((0, H // 3), (H // 3, H)):                       # row bands: right + left
+        band = acc[y0:y1].contiguous()
+        ops.sgm_band(iL, iR, cost[y0:y1].contiguous(), band, H, W, y0, 0, opt, direction, 3, True)
+        acc[y0:y1] = band
+    for x0, x1 in ((0, W // 2 + 1), (W // 2 + 1, W)):               # column bands: down + up
+        band = acc[:, x0:x1].contiguous()
+        ops.sgm_band(iL, iR, cost[:, x0:x1].contiguous(), band, H, W, 0, x0, opt, direction, 12, False)
+        acc[:, x0:x1] = band
+    same(acc[None], want, "sgm2 by bands")
+
+
 def test_transposes_argmin(oracle):
     D, H, W = 13, 17, 29
     rng = np.random.default_rng(5)

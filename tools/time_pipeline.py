@@ -1,0 +1,43 @@
+"""Time the fused pipeline (device-resident inputs) at the bench workload: prints ms per pair.
+
+    ADCENSUS_CBCA_DCH=14 python tools/time_pipeline.py [--iters 10] [--fast]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mccnn_b200  # noqa: E402,F401
+from mccnn_b200 import pipeline  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--fast", action="store_true")
+ap.add_argument("--D", type=int, default=228)
+ap.add_argument("--H", type=int, default=370)
+ap.add_argument("--W", type=int, default=1226)
+ap.add_argument("--C", type=int, default=64)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+opt = pipeline.make_params("kitti", "accurate_cbca4")
+g = torch.Generator(device=dev).manual_seed(0)
+fL = torch.nn.functional.normalize(torch.randn((a.C, a.H, a.W), device=dev, generator=g), dim=0)
+fR = torch.nn.functional.normalize(torch.randn((a.C, a.H, a.W), device=dev, generator=g), dim=0)
+iL = torch.randn((a.H, a.W), device=dev, generator=g)
+iR = torch.randn((a.H, a.W), device=dev, generator=g)
+sp = pipeline.StereoPipeline(a.C, a.D, a.H, a.W, opt)
+if a.fast:
+    sp.set_fast_cbca(True)
+for _ in range(3):
+    sp.run(fL, fR, iL, iR)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.iters):
+    sp.run(fL, fR, iL, iR)
+e1.record()
+torch.cuda.synchronize()
+print("dch=%s ms_per_pair=%.4f" % (os.environ.get("ADCENSUS_CBCA_DCH", "default"), e0.elapsed_time(e1) / a.iters))
+sp.close()
