@@ -135,7 +135,7 @@ def test_sgm2_bands_equal_whole_image(oracle, H, W, D, direction):
     vol = oracle.transpose_dhw_to_hwd(volL if direction == -1 else volR)
     opt = pipeline.make_params("kitti", "fast")
     want = oracle.sgm2(p["imgL"], p["imgR"], vol, opt.pi1, opt.pi2, opt.tau_so, opt.alpha1, opt.sgm_q1, opt.sgm_q2, direction)
-    ops = rowband.CudaOps()
+    ops = rowband.CudaOps(dev())
     iL, iR, cost = cu(p["imgL"]), cu(p["imgR"]), cu(vol)
     acc = torch.zeros_like(cost)
     for y0, y1 in ((0, H // 3), (H // 3, H)):                       # row bands: right + left
