@@ -375,6 +375,7 @@ def run_b200(args):
             "config": {"workload": cfg["name"], "H": cfg["H"], "W": cfg["W"], "D": cfg["D"], "C": cfg["C"],
                        "preset": cfg.get("desc", ""),
                        "pairs_per_gpu_per_step": 1, "parallelism": "pairs sharded over GPUs, no collective",
+                       "schedule": "the two directions of a pair overlapped on two streams (mccnn_pipeline_set_overlap mode 2)",
                        "l2": "per-step working set (0.23 GB features + 1.65 GB volumes) exceeds the 126 MB L2; "
                              "stage timings flush L2 with a 256 MB write"},
             "clocks": clocks,

@@ -186,6 +186,11 @@ void mccnn_pipeline_destroy(mccnn_pipeline *p);
 size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p);
 /* opt-in: use mccnn_cbca_packed_fast for the CBCA iterations (default 0 = exact, bit-identical to the reference) */
 void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on);
+/* opt-in: run the two directions of main.lua:955 concurrently (0 = off: one stream, 4V of volume buffers;
+ * 1 = direction -1 on a side stream with its own 2V + tables, started when direction +1 reaches its SGM phase;
+ * 2 = additionally the permute / SGM phases on high-priority streams).  Results are identical in every mode
+ * (same kernels, same data); only the schedule and the memory footprint change.  Returns 0 or an error. */
+int mccnn_pipeline_set_overlap(mccnn_pipeline *p, int mode);
 /* number of kernel launches one run issues (for bench.py's gpu_launches) */
 int mccnn_pipeline_launches_per_run(const mccnn_pipeline *p);
 

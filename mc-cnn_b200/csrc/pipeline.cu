@@ -1,7 +1,12 @@
 // pipeline.cu -- stereo_predict (main.lua:929-1082, arch 'fast') as one native
 // object: every device buffer is allocated once at create time, a run is a fixed
-// sequence of kernel launches on one stream (no allocation, no host sync), so a
-// batch driver can keep one pipeline per GPU / per stream busy back to back.
+// sequence of kernel launches (no allocation, no host sync) ordered on the caller's
+// stream, so a batch driver can keep one pipeline per GPU / per stream busy back to
+// back.  By default the two independent directions (main.lua:955) are overlapped:
+// direction -1 runs on an internal side stream, started when direction +1 reaches
+// its SGM phase, and the HBM-bound permute / SGM phases run on high-priority
+// streams, so that they share the GPU with the issue-bound CBCA iterations of the
+// other direction (mccnn_pipeline_set_overlap; joined before the LR check).
 //
 // Stage order, which volume is "left"/"right", the direction loop {+1,-1}, the /4
 // and the permutes follow main.lua line by line (cited inline); the kernels are
@@ -41,12 +46,23 @@ struct mccnn_pipeline {
 	float *gauss;     // ks*ks
 	uint8_t *sgmtab;  // SGM penalty-class tables
 	int ks;
+	// direction overlap (mccnn_pipeline_set_overlap): the two directions of main.lua:955 are independent
+	// until the LR check, so the second one runs on a side stream with its own ping-pong / SGM buffers,
+	// started when the first reaches its SGM phase: the HBM-bound permutes + SGM scans of one direction
+	// then share the GPU with the issue-bound CBCA iterations of the other.
+	int overlap;      // 0 off, 1 two streams, 2 additionally the permute/SGM phases on high-priority streams
+	float *bufA2, *bufC2;
+	uint8_t *sgmtab2;
+	cudaStream_t side_stream, hi_stream[2];
+	cudaEvent_t ev_stagger, ev_join, ev_hi_in[2], ev_hi_out[2];
 	// staging for the host-buffer entry points: two slots so that the copy of pair i+1 overlaps
 	// the kernels of pair i
 	float *h_feat[2], *h_img[2], *h_disp[2];  // device copies per slot: 2F, 2HW, HW
 	cudaStream_t own_stream, copy_stream, out_stream;
 	cudaEvent_t ev_in[2], ev_free[2], ev_out[2];
 };
+
+extern "C" int mccnn_pipeline_set_overlap(mccnn_pipeline *p, int mode);
 
 namespace {
 
@@ -104,8 +120,20 @@ extern "C" int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, 
 		return rc;
 	}
 	*out = p;
+	// Default schedule: the two directions overlapped (mode 2), 6V of volume buffers instead of 4V; if the
+	// extra buffers do not fit, the sequential schedule is kept (same results).  ADCENSUS_OVERLAP overrides.
+	const char *e = getenv("ADCENSUS_OVERLAP");
+	const int mode = e ? atoi(e) : 2;
+	rc = mccnn_pipeline_set_overlap(p, mode);
+	if (rc && e) {                                     // an explicit request that cannot be met is an error
+		*out = nullptr;
+		mccnn_pipeline_destroy(p);
+		return rc;
+	}
 	return 0;
 }
+
+static void overlap_release(mccnn_pipeline *p);
 
 extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
 {
@@ -119,6 +147,7 @@ extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
 		if (p->ev_free[k]) cudaEventDestroy(p->ev_free[k]);
 		if (p->ev_out[k]) cudaEventDestroy(p->ev_out[k]);
 	}
+	overlap_release(p);
 	if (p->own_stream) cudaStreamDestroy(p->own_stream);
 	if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
 	if (p->out_stream) cudaStreamDestroy(p->out_stream);
@@ -127,6 +156,56 @@ extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
 
 extern "C" size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p) { return p ? p->bytes : 0; }
 extern "C" void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on) { if (p) p->fast_cbca = on ? 1 : 0; }
+static void overlap_release(mccnn_pipeline *p)
+{
+	const size_t f = sizeof(float);
+	if (p->bufA2) { cudaFree(p->bufA2); p->bytes -= p->V * f; }
+	if (p->bufC2) { cudaFree(p->bufC2); p->bytes -= p->V * f; }
+	if (p->sgmtab2) { cudaFree(p->sgmtab2); p->bytes -= adc_sgm_table_bytes(p->H, p->W, p->D); }
+	p->bufA2 = p->bufC2 = nullptr;
+	p->sgmtab2 = nullptr;
+	if (p->side_stream) cudaStreamDestroy(p->side_stream);
+	if (p->ev_stagger) cudaEventDestroy(p->ev_stagger);
+	if (p->ev_join) cudaEventDestroy(p->ev_join);
+	p->side_stream = nullptr; p->ev_stagger = nullptr; p->ev_join = nullptr;
+	for (int k = 0; k < 2; k++) {
+		if (p->hi_stream[k]) cudaStreamDestroy(p->hi_stream[k]);
+		if (p->ev_hi_in[k]) cudaEventDestroy(p->ev_hi_in[k]);
+		if (p->ev_hi_out[k]) cudaEventDestroy(p->ev_hi_out[k]);
+		p->hi_stream[k] = nullptr; p->ev_hi_in[k] = nullptr; p->ev_hi_out[k] = nullptr;
+	}
+	p->overlap = 0;
+}
+
+extern "C" int mccnn_pipeline_set_overlap(mccnn_pipeline *p, int mode)
+{
+	if (!p || mode < 0 || mode > 2) return ADCENSUS_EINVAL;
+	DeviceGuard g(p->device);
+	if (mode && !p->side_stream) {
+		const size_t f = sizeof(float);
+		int rc = 0, lo = 0, hi = 0;
+		if (!rc) rc = dev_alloc((void **)&p->bufA2, p->V * f, &p->bytes);
+		if (!rc) rc = dev_alloc((void **)&p->bufC2, p->V * f, &p->bytes);
+		if (!rc) rc = dev_alloc((void **)&p->sgmtab2, adc_sgm_table_bytes(p->H, p->W, p->D), &p->bytes);
+		if (!rc) rc = (int)cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
+		if (!rc) rc = (int)cudaStreamCreateWithPriority(&p->side_stream, cudaStreamNonBlocking, lo);
+		for (int k = 0; k < 2 && !rc; k++) {
+			rc = (int)cudaStreamCreateWithPriority(&p->hi_stream[k], cudaStreamNonBlocking, hi);
+			if (!rc) rc = (int)cudaEventCreateWithFlags(&p->ev_hi_in[k], cudaEventDisableTiming);
+			if (!rc) rc = (int)cudaEventCreateWithFlags(&p->ev_hi_out[k], cudaEventDisableTiming);
+		}
+		if (!rc) rc = (int)cudaEventCreateWithFlags(&p->ev_stagger, cudaEventDisableTiming);
+		if (!rc) rc = (int)cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
+		if (rc) {                                      // leave the pipeline as it was (sequential mode still works)
+			overlap_release(p);
+			cudaGetLastError();
+			return rc;
+		}
+	}
+	p->overlap = mode;
+	return 0;
+}
+
 extern "C" int mccnn_pipeline_launches_per_run(const mccnn_pipeline *p) { return p ? p->launches : 0; }
 
 #define STEP(call)                 \
@@ -162,34 +241,57 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 
 	float *dispR = p->maps, *dispL = p->maps + HW;
 	float *final_left = nullptr;
-	float *spare = p->bufA;
-	const int directions[2] = {1, -1};                                                           // :955
-	for (int k = 0; k < 2; k++) {
-		const int direction = directions[k];
-		float *cur = direction == -1 ? volsL : volsR;                                            // :986
+	// One direction of main.lua:955-1051 on stream `ds`: cur/spare ping-pong, acc = SGM accumulator.
+	// k = 0: direction +1 (right volume), k = 1: direction -1 (left volume).
+	auto run_direction = [&](int k, cudaStream_t ds, float *cur, float *spare, float *acc, uint8_t *tab) -> int {
+		const int direction = k == 0 ? 1 : -1;                                                   // :955
 		for (int i = 0; i < o.cbca_i1; i++) {                                                    // :998-1001
-			STEP(adc_cbca_packed(p->packed, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, s, p->fast_cbca));
+			STEP(adc_cbca_packed(p->packed, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, ds, p->fast_cbca));
 			float *t = cur; cur = spare; spare = t; nl += 1;
+		}
+		if (k == 0 && p->overlap) STEP((int)cudaEventRecord(p->ev_stagger, ds));                 // the other direction may start
+		cudaStream_t ss = ds;                                                                    // stream of the permute/SGM phase
+		if (p->overlap == 2 && o.sgm_i > 0) {
+			ss = p->hi_stream[k];
+			STEP((int)cudaEventRecord(p->ev_hi_in[k], ds));
+			STEP((int)cudaStreamWaitEvent(ss, p->ev_hi_in[k], 0));
 		}
 		for (int it = 0; it < o.sgm_i; it++) {                                                   // :1008-1020
-			STEP(mccnn_transpose_dhw_to_hwd(cur, spare, D, H, W, s));                            // :1008
-			STEP(adc_sgm2(imgL, imgR, spare, p->bufC, p->sgmtab, H, W, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
-				      o.sgm_q1, o.sgm_q2, direction, /*zero_out=*/true, s));                     // :1014-1016
-			STEP(mccnn_transpose_hwd_to_dhw_div4(p->bufC, cur, D, H, W, s));                     // :1017-1020
+			STEP(mccnn_transpose_dhw_to_hwd(cur, spare, D, H, W, ss));                           // :1008
+			STEP(adc_sgm2(imgL, imgR, spare, acc, tab, H, W, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
+				      o.sgm_q1, o.sgm_q2, direction, /*zero_out=*/true, ss));                    // :1014-1016
+			STEP(mccnn_transpose_hwd_to_dhw_div4(acc, cur, D, H, W, ss));                        // :1017-1020
 			nl += 7;
 		}
+		if (ss != ds) {
+			STEP((int)cudaEventRecord(p->ev_hi_out[k], ss));
+			STEP((int)cudaStreamWaitEvent(ds, p->ev_hi_out[k], 0));
+		}
 		for (int i = 0; i < o.cbca_i2; i++) {                                                    // :1035-1038
-			STEP(adc_cbca_packed(p->packed, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, s, p->fast_cbca));
+			STEP(adc_cbca_packed(p->packed, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, ds, p->fast_cbca));
 			float *t = cur; cur = spare; spare = t; nl += 1;
 		}
-		STEP(mccnn_argmin(cur, direction == 1 ? dispR : dispL, D, (int)HW, s)); nl += 1;         // :1049-1050
+		STEP(mccnn_argmin(cur, direction == 1 ? dispR : dispL, D, (int)HW, ds)); nl += 1;        // :1049-1050
 		float *dst = direction == 1 ? volR : volL;                                               // :1042-1047
-		if (dst) {
-			STEP((int)cudaMemcpyAsync(dst, cur, V * sizeof(float), cudaMemcpyDeviceToDevice, s));
-		}
+		if (dst) STEP((int)cudaMemcpyAsync(dst, cur, V * sizeof(float), cudaMemcpyDeviceToDevice, ds));
 		if (direction == -1) final_left = cur;
-		// the right volume is dead after its argmin: both of its buffers may serve as spares,
-		// `spare` already points at a free one
+		return 0;
+	};
+	if (!p->overlap) {
+		// sequential: the right volume is dead after its argmin, so both of its buffers serve the
+		// left direction as spares (4V of volume buffers in total)
+		STEP(run_direction(0, s, volsR, p->bufA, p->bufC, p->sgmtab));
+		// after direction +1, `bufA` or `volsR` is free whichever ended up as its spare: recompute
+		const int flips = o.cbca_i1 + o.cbca_i2;                                                 // ping-pong swaps of direction +1
+		STEP(run_direction(1, s, volsL, (flips & 1) ? volsR : p->bufA, p->bufC, p->sgmtab));
+	} else {
+		// concurrent: direction -1 on the side stream with its own spare / accumulator / tables,
+		// started when direction +1 leaves its first CBCA block
+		STEP(run_direction(0, s, volsR, p->bufA, p->bufC, p->sgmtab));
+		STEP((int)cudaStreamWaitEvent(p->side_stream, p->ev_stagger, 0));
+		STEP(run_direction(1, p->side_stream, volsL, p->bufA2, p->bufC2, p->sgmtab2));
+		STEP((int)cudaEventRecord(p->ev_join, p->side_stream));
+		STEP((int)cudaStreamWaitEvent(s, p->ev_join, 0));
 	}
 
 	float *m = p->maps;

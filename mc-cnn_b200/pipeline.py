@@ -153,6 +153,10 @@ class StereoPipeline:
         except Exception:
             pass
 
+    def set_overlap(self, mode=1):
+        """Run the two directions concurrently on two streams (mccnn_pipeline_set_overlap); results are unchanged."""
+        adcensus._check(adcensus.lib().mccnn_pipeline_set_overlap(self._h, int(mode)), "mccnn_pipeline_set_overlap")
+
     def set_fast_cbca(self, on=True):
         """Opt in to the approximate CBCA kernel (prefix sums per support row: ~1e-6 relative to the
         exact-order kernel, not bit-exact with the reference).  Default is exact."""
