@@ -58,6 +58,15 @@ PRESETS = {
                                 alpha1=1.25, tau_so=0.08, blur_sigma=4.64, blur_t=5, border=4, lr_check=1),
     ("mb", "fast"): dict(L1=0, tau1=0, cbca_i1=0, cbca_i2=0, pi1=2.3, pi2=24.3, sgm_q1=4, sgm_q2=2,
                          alpha1=1.5, tau_so=0.08, blur_sigma=6, blur_t=2, border=5, lr_check=0),
+    # net-free cost volumes (main.lua:146-204): no feature tower, hence no fix_border (border = 0)
+    ("kitti", "census"): dict(L1=0, tau1=0.01, cbca_i1=4, cbca_i2=8, pi1=4, pi2=128.0, sgm_q1=3, sgm_q2=3.5,
+                              alpha1=1.25, tau_so=1.0, blur_sigma=7.74, blur_t=6, border=0, lr_check=1),
+    ("mb", "census"): dict(L1=5, tau1=0.22, cbca_i1=8, cbca_i2=8, pi1=4.0, pi2=32.0, sgm_q1=4, sgm_q2=3,
+                           alpha1=1.5, tau_so=1.0, blur_sigma=2.78, blur_t=3, border=0, lr_check=0),
+    ("kitti", "ad"): dict(L1=3, tau1=0.03, cbca_i1=0, cbca_i2=4, pi1=0.76, pi2=13.93, sgm_q1=3.5, sgm_q2=2,
+                          alpha1=2.5, tau_so=0.01, blur_sigma=7.74, blur_t=6, border=0, lr_check=1),
+    ("mb", "ad"): dict(L1=5, tau1=0.36, cbca_i1=0, cbca_i2=4, pi1=0.4, pi2=8.0, sgm_q1=3, sgm_q2=4,
+                       alpha1=2.5, tau_so=0.08, blur_sigma=7.74, blur_t=1, border=0, lr_check=0),
     # BASELINE.json config 3 ("KITTI accurate: CBCA x4 + SGM"): kitti slow post-processing with
     # cbca_i1 = cbca_i2 = 2
     ("kitti", "accurate_cbca4"): dict(L1=5, tau1=0.13, cbca_i1=2, cbca_i2=2, pi1=1.32, pi2=24.25, sgm_q1=3,
@@ -73,20 +82,32 @@ def make_params(dataset="kitti", arch="fast", **overrides):
     return Params(**d)
 
 
-def stereo_predict(x_batch, features, opt, disp_max, want_vols=False):
-    """main.lua:929-1082 (arch == 'fast') through the adcensus.* operators.
+def stereo_predict(x_batch, features, opt, disp_max, want_vols=False, arch="fast"):
+    """main.lua:929-1082 through the adcensus.* operators.
 
-    x_batch  (2,1,H,W) standardised images (left, right); features (2,C,H,W) the tower
-    output (unit-norm); opt a :class:`Params`.  Returns disp (1,1,H,W) [, left vol, right vol].
+    x_batch  (2,1,H,W) standardised images (left, right); arch 'fast': features (2,C,H,W) the tower
+    output (unit-norm); arch 'ad' / 'census': the matching cost comes from the images themselves
+    (main.lua:932-942), `features` is ignored.  opt a :class:`Params`.
+    Returns disp (1,1,H,W) [, left vol, right vol].
     """
-    assert x_batch.is_cuda and features.is_cuda
+    assert x_batch.is_cuda
     H, W = x_batch.size(2), x_batch.size(3)
     dev = x_batch.device
     vols = torch.empty((2, disp_max, H, W), device=dev, dtype=torch.float32)
-    adcensus.fill_nan(vols)                                                       # :946
-    adcensus.StereoJoin(features[0:1], features[1:2], vols[0:1], vols[1:2])       # :947
-    adcensus.fix_border(vols[0:1], opt.border, -1)                                # :948
-    adcensus.fix_border(vols[1:2], opt.border, 1)                                 # :949
+    adcensus.fill_nan(vols)                                                       # :933 / :939 / :946
+    if arch == "ad":
+        adcensus.ad(x_batch[0:1], x_batch[1:2], vols[0:1], -1)                    # :934
+        adcensus.ad(x_batch[1:2], x_batch[0:1], vols[1:2], 1)                     # :935
+    elif arch == "census":
+        adcensus.census(x_batch[0:1], x_batch[1:2], vols[0:1], -1)                # :940
+        adcensus.census(x_batch[1:2], x_batch[0:1], vols[1:2], 1)                 # :941
+    elif arch == "fast":
+        assert features is not None and features.is_cuda
+        adcensus.StereoJoin(features[0:1], features[1:2], vols[0:1], vols[1:2])   # :947
+        adcensus.fix_border(vols[0:1], opt.border, -1)                            # :948
+        adcensus.fix_border(vols[1:2], opt.border, 1)                             # :949
+    else:
+        raise ValueError("arch must be 'fast', 'ad' or 'census' (the 'slow' scorer head is outside libadcensus)")
 
     disp = {}
     out_vols = {}

@@ -245,3 +245,46 @@ def stereo_predict(featL, featR, imgL, imgR, D, params, want_vols=False):
     if rc != 0:
         raise ValueError("orc_stereo_predict: bad arguments")
     return (disp, volL, volR) if want_vols else disp
+
+
+def stereo_predict_chain(imgL, imgR, D, params, arch="fast", featL=None, featR=None, want_vols=False):
+    """main.lua:929-1082 composed from the per-operator oracle functions (the C `orc_stereo_predict`
+    is the same chain for arch 'fast' in one call; tests/test_oracle_properties.py checks that the
+    two agree).  arch 'ad' / 'census' (main.lua:932-942) build the volumes from the images.
+    Returns disp (H,W) [, volL, volR (D,H,W)]."""
+    imgL, imgR = _f(imgL), _f(imgR)
+    H, W = imgL.shape
+    if arch == "ad":
+        volL, volR = ad(imgL, imgR, D, -1), ad(imgR, imgL, D, 1)                   # :934-935
+    elif arch == "census":
+        volL, volR = census(imgL, imgR, D, -1), census(imgR, imgL, D, 1)           # :940-941
+    elif arch == "fast":
+        volL, volR = stereo_join(featL, featR, D)                                  # :946-947
+        fix_border(volL, params.border, -1)                                        # :948
+        fix_border(volR, params.border, 1)                                         # :949
+    else:
+        raise ValueError(arch)
+    x0c, x1c = cross(imgL, params.L1, params.tau1), cross(imgR, params.L1, params.tau1)   # :995-996
+    disp = {}
+    vols = {}
+    for direction in (1, -1):                                                      # :955
+        vol = volL if direction == -1 else volR                                    # :986
+        for _ in range(params.cbca_i1):                                            # :998-1001
+            vol = cbca(x0c, x1c, vol, direction)
+        for _ in range(params.sgm_i):                                              # :1008-1020
+            out = sgm2(imgL, imgR, transpose_dhw_to_hwd(vol), params.pi1, params.pi2, params.tau_so, params.alpha1,
+                       params.sgm_q1, params.sgm_q2, direction)
+            vol = transpose_hwd_to_dhw_div4(out)
+        for _ in range(params.cbca_i2):                                            # :1035-1038
+            vol = cbca(x0c, x1c, vol, direction)
+        vols[direction] = vol
+        disp[direction] = spatial_argmin(vol) - 1                                  # :1049-1050
+    d = disp[-1]
+    if params.lr_check:                                                            # :1054-1066
+        outlier = outlier_detection(disp[-1], disp[1], D)
+        d = interpolate_occlusion(d, outlier)
+        d = interpolate_mismatch(d, outlier)
+    d = subpixel_enchancement(d, vols[-1], D)                                      # :1068
+    d = median2d(d, 5)                                                             # :1073
+    d = mean2d(d, gaussian(params.blur_sigma), params.blur_t)                      # :1078
+    return (d, vols[-1], vols[1]) if want_vols else d

@@ -291,6 +291,55 @@ def test_pipeline_vs_oracle(oracle, H, W, C, D, preset, over):
     sp.close()
 
 
+def _shifted_views(H, W, shift, seed):
+    """two views of one textured image, the left one shifted by `shift` pixels, one gain / offset for both"""
+    base = synth.natural_image(np.random.default_rng(seed), H, W + shift)
+    base = ((base - base.mean()) / base.std(ddof=1)).astype(np.float32)
+    return np.ascontiguousarray(base[:, :W]), np.ascontiguousarray(base[:, shift:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dataset,arch,H,W,D", [("kitti", "census", 24, 70, 10), ("kitti", "ad", 20, 64, 12),
+                                                ("mb", "census", 18, 50, 9), ("mb", "ad", 16, 48, 8)])
+def test_pipeline_ad_census_vs_oracle(oracle, dataset, arch, H, W, D):
+    """main.lua:932-942: the net-free archs through the same operator chain, bit-identical to the oracle"""
+    imgL, imgR = _shifted_views(H, W, 4, seed=H + D)
+    opt = pipeline.make_params(dataset, arch)
+    want, wantL, wantR = oracle.stereo_predict_chain(imgL, imgR, D, oracle.Params(**opt.as_dict()), arch, want_vols=True)
+    xb = cu(np.stack([imgL, imgR])[:, None])
+    got, gotL, gotR = pipeline.stereo_predict(xb, None, opt, D, want_vols=True, arch=arch)
+    same(gotL, wantL, arch + " left volume")
+    same(gotR, wantR, arch + " right volume")
+    same(got, want, arch + " disp")
+
+
+@pytest.mark.gpu
+def test_frontend_predict_from_png_files(oracle, tmp_path):
+    """frontend.predict: PNG pair -> standardised batch -> census chain -> right.bin, left.bin, disp.bin"""
+    from PIL import Image
+
+    from mccnn_b200 import frontend
+
+    H, W, D, shift = 30, 80, 12, 5
+    base = synth.natural_image(np.random.default_rng(21), H, W + shift)
+    u8 = np.clip((base - base.min()) / (base.max() - base.min()) * 255.0, 0, 255).astype(np.uint8)
+    lp, rp = str(tmp_path / "l.png"), str(tmp_path / "r.png")
+    Image.fromarray(np.stack([u8[:, :W]] * 3, axis=2), "RGB").save(lp)          # colour file: exercises rgb2y
+    Image.fromarray(u8[:, shift:], "L").save(rp)
+    out = tmp_path / "out"
+    disp = frontend.predict(lp, rp, "kitti", "census", disp_max=D, out_dir=str(out))
+    batch = frontend.make_batch(lp, rp)
+    opt = pipeline.make_params("kitti", "census")
+    want, wantL, wantR = oracle.stereo_predict_chain(batch[0, 0], batch[1, 0], D, oracle.Params(**opt.as_dict()),
+                                                     "census", want_vols=True)
+    same(disp, want, "predict disp")
+    assert (np.abs(disp[:, 2 * D:] - shift) < 1.0).mean() > 0.9                 # and it is the right answer
+    for name, ref, n in (("right.bin", wantR, D * H * W), ("left.bin", wantL, D * H * W), ("disp.bin", want, H * W)):
+        data = np.fromfile(str(out / name), "<f4")
+        assert data.size == n
+        same(data, ref.ravel(), name)
+
+
 def test_against_golden(golden_dir):
     files = sorted(glob.glob(os.path.join(golden_dir, "pipe_*.npz")))
     if not files:

@@ -102,3 +102,40 @@ def test_median_and_mean_border_handling(oracle):
     assert k.shape == (5, 5) and k[2, 2] == 1.0
     out = oracle.mean2d(img, k, 1000.0)
     assert np.isfinite(out).all() and abs(out[2, 2] - img[2, 2]) < 1.0
+
+
+def test_chain_composition_equals_monolith(oracle):
+    """oracle.stereo_predict_chain (per-operator composition, also the ad / census vehicle) must give
+    exactly what the one-call C chain gives for arch 'fast'."""
+    H, W, C, D = 24, 60, 8, 12
+    p = synth.make_pair(H, W, C, D, seed=5)
+    for preset in (("kitti", "fast"), ("kitti", "accurate_cbca4"), ("mb", "fast")):
+        prm = oracle.Params(**pipeline.make_params(*preset).as_dict())
+        a = oracle.stereo_predict(p["featL"], p["featR"], p["imgL"], p["imgR"], D, prm, want_vols=True)
+        b = oracle.stereo_predict_chain(p["imgL"], p["imgR"], D, prm, "fast", p["featL"], p["featR"], want_vols=True)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y, equal_nan=True), preset
+
+
+def test_ad_census_chain_invariants(oracle):
+    """main.lua:932-942: net-free volumes.  NaN triangles as for StereoJoin, census costs are counts
+    of differing bits / channel in [0, 81], the chain returns a finite map in range and recovers a
+    constant shift of a textured image."""
+    H, W, D, shift = 40, 96, 12, 5
+    rng = np.random.default_rng(7)
+    base = synth.natural_image(rng, H, W + shift)
+    base = ((base - base.mean()) / base.std(ddof=1)).astype(np.float32)   # one gain/offset for both views (AD is not invariant)
+    imgL, imgR = base[:, :W].copy(), base[:, shift:].copy()      # left pixel x shows what right pixel x - shift shows
+    vc = oracle.census(imgL, imgR, D, -1)
+    va = oracle.ad(imgL, imgR, D, -1)
+    for d in range(D):
+        for v in (vc, va):
+            assert np.isnan(v[d, :, :d]).all() and not np.isnan(v[d, :, d:]).any()
+    assert vc[~np.isnan(vc)].min() >= 0 and vc[~np.isnan(vc)].max() <= 81 and np.all(vc[~np.isnan(vc)] == np.round(vc[~np.isnan(vc)]))
+    assert va[~np.isnan(va)].min() >= 0
+    for arch in ("census", "ad"):
+        prm = oracle.Params(**pipeline.make_params("kitti", arch).as_dict())
+        disp = oracle.stereo_predict_chain(imgL, imgR, D, prm, arch)
+        assert disp.shape == (H, W) and not np.isnan(disp).any()
+        assert disp.min() >= 0 and disp.max() <= D - 1 + 1e-3
+        assert (np.abs(disp[:, 2 * D:] - shift) < 1.0).mean() > 0.9, arch
