@@ -11,7 +11,7 @@ PIL = pytest.importorskip("PIL.Image")
 
 def _png(tmp_path, name, arr, mode):
     p = tmp_path / name
-    PIL.fromarray(arr, mode).save(p)
+    PIL.fromarray(arr).save(p)  # mode follows dtype / shape (L, RGB, RGBA)
     return str(p)
 
 

@@ -324,8 +324,8 @@ def test_frontend_predict_from_png_files(oracle, tmp_path):
     base = synth.natural_image(np.random.default_rng(21), H, W + shift)
     u8 = np.clip((base - base.min()) / (base.max() - base.min()) * 255.0, 0, 255).astype(np.uint8)
     lp, rp = str(tmp_path / "l.png"), str(tmp_path / "r.png")
-    Image.fromarray(np.stack([u8[:, :W]] * 3, axis=2), "RGB").save(lp)          # colour file: exercises rgb2y
-    Image.fromarray(u8[:, shift:], "L").save(rp)
+    Image.fromarray(np.stack([u8[:, :W]] * 3, axis=2)).save(lp)          # colour file: exercises rgb2y
+    Image.fromarray(np.ascontiguousarray(u8[:, shift:])).save(rp)
     out = tmp_path / "out"
     disp = frontend.predict(lp, rp, "kitti", "census", disp_max=D, out_dir=str(out))
     batch = frontend.make_batch(lp, rp)
