@@ -596,6 +596,7 @@ int adc_sgm2_band(const float *in, float *out, const uint8_t *tab, int H, int W,
 	const int pad = sgm_slots(D);
 	if (pass_mask & 12) {                              // vertical scans: band = whole columns (H == Ht)
 		unsigned *sel = reinterpret_cast<unsigned *>(const_cast<uint8_t *>(tab) + sgm_sel_offset(Ht, Wt + 2 * pad));
+		if (Ht > 65535) return ADCENSUS_ELIMIT;            // gridDim.y
 		const dim3 grid(adc_div_up(W, 8), Ht), block(32, 8);
 		switch (pad / 32) {
 		case 1: sgm_sel_kernel<1><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
