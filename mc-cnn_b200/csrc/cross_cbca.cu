@@ -100,12 +100,13 @@ __device__ __forceinline__ unsigned long long adc_fma2(unsigned long long a, uns
 // columns and the row's combined horizontal arms (L, R_), and masks the window ONCE: slots outside
 // the run (x - L, x + R_) become +0.0f (one compare + one select per slot, shared by every output
 // that uses this row).  Every output whose vertical arm may contain the row then accumulates
-// acc = fmaf(wm[k], q, acc) in column order with q in {0.0f, 1.0f} (row inside its vertical arm,
+// acc = fmaf(wm[k], q, acc) (two outputs per FFMA2, see the kernel body) in column order with q in {0.0f, 1.0f} (row inside its vertical arm,
 // adcensus.cu:361): no predicates (nine live outputs per row would spill the 7 predicate registers).
 // Exactness: fmaf(w, 1, acc) is acc + w (one rounding of the same real number); fmaf(w, 0, acc)
 // adds +-0.0f to an accumulator that is never -0.0f (it starts at +0.0f and a sum is -0.0f only
 // if both operands are) => acc unchanged.  (Moving the masks to FADD.SAT/FMUL on the FMA pipe and
-// the arm minima to VIMNMX.U16x2 was measured slower: 1.15 ms vs 1.02 ms.)  The order of the real
+// the arm minima to VIMNMX.U16x2 was measured slower: 1.15 ms vs 1.02 ms with scalar FFMA; the
+// FFMA2 pairing took 1.02 ms to 0.92 ms.)  The order of the real
 // additions per output is rows ascending, columns ascending => bit-identical to adcensus.cu:361-370.
 // The masks are selects, so NaNs of the invalid triangle (never inside a run) are dropped; the
 // accumulation itself needs finite values inside the runs, i.e. a volume that is finite on its

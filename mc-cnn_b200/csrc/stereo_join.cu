@@ -8,7 +8,7 @@
 //     (x, j = x - d) space that chunk is a parallelogram; it is covered by 8x x 16j
 //     register tiles laid along the diagonal (16 x-groups, NS tiles each, 6% of the
 //     tile entries fall outside the band and are discarded), so the inner loop is a
-//     plain outer product: per channel 2 LDS.128 of L + 4 LDS.128 of R for 128 FFMA;
+//     plain outer product: per channel 2 LDS.128 of L + 4 LDS.128 of R for 128 FMAs (64 FFMA2);
 //   * operands are stored in shared memory "split-plane" (the low and the high float4
 //     of every 8-float group in separate planes), which makes every quarter-warp of
 //     an LDS.128 read 128 contiguous bytes: no bank conflicts (the naive layout is
