@@ -128,6 +128,8 @@ def sgm2(x0, x1, vol_hwd, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction, o
     """vol_hwd: (H,W,D).  Accumulates into `out` (zeros if None) and returns it."""
     x0, x1, vol_hwd = _f(x0), _f(x1), _f(vol_hwd)
     H, W, D = vol_hwd.shape
+    if H > W:
+        raise ValueError("sgm2: the reference's line-state scratch is (W, D) and indexed by row too (main.lua:1012, adcensus.cu:576): H <= W required")
     if out is None:
         out = np.zeros_like(vol_hwd)
     tmp = np.empty((W, D), np.float32)
