@@ -81,6 +81,9 @@ int mccnn_cbca_packed(const void *packed, const float *x0c, const float *x1c, co
  * from per-row prefix sums and added as one value (same region, same row order, different rounding;
  * ~1e-6 relative, NaN positions identical; arms up to 5 pixels, longer arms fall back to the exact
  * kernels).  About 2.5x fewer instructions than the exact-order kernel, which is issue-bound. */
+/* level 0 / 1 / 2 as in mccnn_pipeline_set_fast_cbca */
+int mccnn_cbca_packed_level(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+			    int D, int H, int W, int direction, int max_arm, int level, adcensus_stream_t stream);
 int mccnn_cbca_packed_fast(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 			   int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream);
 
@@ -184,7 +187,9 @@ int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, int W,
 			  const mccnn_params *params, int device);
 void mccnn_pipeline_destroy(mccnn_pipeline *p);
 size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p);
-/* opt-in: use mccnn_cbca_packed_fast for the CBCA iterations (default 0 = exact, bit-identical to the reference) */
+/* opt-in: approximate CBCA for the pipeline's iterations.  0 (default) = exact, bit-identical to the reference;
+ * 1 = mccnn_cbca_packed_fast (per-row prefix sums, ~1e-6 relative); 2 = EXPERIMENTAL constant-work kernel (prefix sums
+ * along x and y, mccnn_cbca_packed_level(..., 2)), not yet validated on hardware. */
 void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on);
 /* opt-in: run the two directions of main.lua:955 concurrently (0 = off: one stream, 4V of volume buffers;
  * 1 = direction -1 on a side stream with its own 2V + tables, started when direction +1 reaches its SGM phase;

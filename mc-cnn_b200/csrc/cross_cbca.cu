@@ -335,6 +335,183 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 	}
 }
 
+// ------------------------------------------------------------------ cbca, constant work per pixel (opt-in level 2)
+// EXPERIMENTAL until validated on the GPU (mccnn_pipeline_set_fast_cbca(p, 2) / fast == 2): NOT bit-exact by
+// construction, aimed at the north star's 1e-4 bar for float aggregation.  Numerical model and CPU tests:
+// oracle/cbca_prefix_model.py, tests/test_cbca_prefix_model.py (2.5e-6 relative after four iterations).
+//
+// The run of a support row depends on (d, row, column) only, not on which output row uses it:
+//     S(r, x) = I(r, x + R_ - 1) - I(r, x - L)           I = inclusive prefix of the tile row (NaN -> 0)
+//     out(y, x) = (T(y + D - 1, x) - T(y - U, x)) / (N(y + D - 1, x) - N(y - U, x))
+// with T, N the inclusive prefixes of S and of the run lengths along the rows.  All prefixes are local to the
+// 32 x 128 tile (+ halo), which bounds the cancellation error.  Per plane: combined arms straight from the
+// (L2-resident) packed arm images, row scan in place on the double-buffered plane tile, run sums, column scan
+// (run sums on warps 0-3, run lengths on warps 4-7), outputs: ~75 instructions per output, five barriers.
+template <int R>
+struct O1Cfg {
+	// An arm LENGTH is the distance to the first EXCLUDED pixel, so lengths reach R + 1 while the support only
+	// reaches R pixels out.  The prefix differences index that excluded pixel (I(x - L), T(y - U)): the tile
+	// therefore carries one extra row above and one extra column to the left of the R-pixel halo.
+	static constexpr int TH = CW_TY + 2 * R + 1;   // image rows y0 - R - 1 .. y0 + CW_TY + R - 1
+	static constexpr int TWP = CW_TX + 2 * R + 1;  // image columns x0 - R - 1 .. x0 + CW_TX + R - 1 (odd pitch)
+	static constexpr int SMEM = (TH * CW_TX + 2 * TH * TWP + 2 * TH * CW_TX) * 4;
+};
+
+template <int R>
+__global__ void __launch_bounds__(CW_NT, (O1Cfg<R>::SMEM <= 110 * 1024) ? 2 : 1)
+cbca_o1_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
+	       const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction, int dch)
+{
+	using Cfg = O1Cfg<R>;
+	constexpr int TH = Cfg::TH, TWP = Cfg::TWP;
+	extern __shared__ __align__(16) uint32_t cw_smem[];
+	uint32_t *scomb = cw_smem;                                     // [TH][CW_TX] combined arms of the current d
+	float *svbuf = reinterpret_cast<float *>(scomb + TH * CW_TX);  // 2 x [TH][TWP] plane tile + halo, scanned in place
+	float *sS = svbuf + 2 * TH * TWP;                              // [TH][CW_TX] run sums, then their prefix along rows
+	float *sN = sS + TH * CW_TX;                                   // [TH][CW_TX] run lengths, then their prefix
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int x0 = blockIdx.x * CW_TX, y0 = blockIdx.y * CW_TY, d0 = blockIdx.z * dch;
+	const int dn = min(dch, D - d0);
+	const long HW = (long)H * W;
+	const int cx = 32 * (warp & 3) + lane;
+	const int ry = CW_NVT * (warp >> 2);
+	const int x = x0 + cx;
+	constexpr int NW = CW_NT / 32;
+
+	int nproc = 0;   // disparities whose tile is not entirely inside the invalid triangle (a prefix of the chunk)
+	while (nproc < dn && !(direction < 0 ? (x0 + CW_TX - 1 - (d0 + nproc) < 0) : (x0 + d0 + nproc >= W))) nproc++;
+
+	auto issue_tile = [&](int d, float *buf) {
+		const float *plane = vol + (long)d * HW;
+		for (int r = warp; r < TH; r += NW) {
+			const int yy = y0 - R - 1 + r;
+			const bool rowok = yy >= 0 && yy < H;
+			const float *grow = plane + (long)(rowok ? yy : 0) * W;
+#pragma unroll
+			for (int m = 0; m < (TWP + 31) / 32; m++) {
+				const int c = lane + 32 * m, xx = x0 - R - 1 + c;
+				if (c < TWP) {
+					const bool ok = rowok && xx >= 0 && xx < W;
+					const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + r * TWP + c);
+					const int nbytes = ok ? 4 : 0;
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(grow + (ok ? xx : 0)), "r"(nbytes));
+				}
+			}
+		}
+	};
+	if (nproc > 0) {
+		issue_tile(d0, svbuf);
+		asm volatile("cp.async.commit_group;");
+	}
+	for (int dd = 0; dd < nproc; dd++) {
+		const int d = d0 + dd;
+		const int sh = d * direction;
+		const int xs = x + sh;
+		const bool valid_col = x < W && xs >= 0 && xs < W;
+		float *sv = svbuf + (dd & 1) * TH * TWP;
+		__syncthreads();                               // every reader of the previous plane's arrays is done
+		if (dd + 1 < nproc) issue_tile(d + 1, svbuf + ((dd + 1) & 1) * TH * TWP);
+		asm volatile("cp.async.commit_group;");
+		// combined arms: byte-wise min of the left arms at x and the right arms at x + d*dir (0 outside the image)
+		for (int r = warp; r < TH; r += NW) {
+			const int yy = y0 - R - 1 + r;
+			const bool rowok = yy >= 0 && yy < H;
+#pragma unroll
+			for (int m = 0; m < CW_TX / 32; m++) {
+				const int c = lane + 32 * m, xx = x0 + c, xr = xx + sh;
+				const uint32_t a = (rowok && xx < W) ? __ldg(a0g + (long)yy * W + xx) : 0u;
+				const uint32_t b = (rowok && xr >= 0 && xr < W) ? __ldg(a1g + (long)yy * W + xr) : 0u;
+				scomb[r * CW_TX + c] = __vminu4(a, b);
+			}
+		}
+		asm volatile("cp.async.wait_group 1;");        // the tile of d has landed (d + 1 may still be in flight)
+		__syncthreads();
+
+		// 1. inclusive prefix of every tile row, in place; NaN (invalid triangle, never inside a run) counts as 0
+		constexpr int EPL = (TWP + 31) / 32;
+		for (int r = warp; r < TH; r += NW) {
+			float loc[EPL];
+			float run = 0.0f;
+#pragma unroll
+			for (int i = 0; i < EPL; i++) {
+				const int c = lane * EPL + i;
+				float v = c < TWP ? sv[r * TWP + c] : 0.0f;
+				v = v == v ? v : 0.0f;
+				run += v;
+				loc[i] = run;
+			}
+			float incl = run;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const float up = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o) incl += up;
+			}
+			const float base = incl - run;
+#pragma unroll
+			for (int i = 0; i < EPL; i++) {
+				const int c = lane * EPL + i;
+				if (c < TWP) sv[r * TWP + c] = base + loc[i];
+			}
+		}
+		__syncthreads();
+
+		// 2. sum and length of the run (x - L, x + R_) of every tile row at this thread's column (:362-369)
+		for (int r = warp >> 2; r < TH; r += 2) {
+			const uint32_t c = scomb[r * CW_TX + cx];
+			const int L = c & 255, Rr = (c >> 8) & 255;
+			const float *I = sv + r * TWP + cx + R + 1;   // I[k]: inclusive prefix at image column x + k (k >= -R - 1)
+			float S = 0.0f, C = 0.0f;
+			if (L > 0) {                               // 0 = pixel outside either image
+				S = I[Rr - 1] - I[-L];
+				C = (float)(L + Rr - 1);
+			}
+			sS[r * CW_TX + cx] = S;
+			sN[r * CW_TX + cx] = C;
+		}
+		__syncthreads();
+
+		// 3. inclusive prefixes along the rows: run sums on warps 0-3, run lengths on warps 4-7
+		{
+			float *col = (warp < 4 ? sS : sN) + cx;
+			float run = 0.0f;
+#pragma unroll 8
+			for (int r = 0; r < TH; r++) {
+				run += col[r * CW_TX];
+				col[r * CW_TX] = run;
+			}
+		}
+		__syncthreads();
+
+		// 4. outputs: rows y - U + 1 .. y + Dn - 1 of the column (:359-361, :373)
+#pragma unroll
+		for (int oy = 0; oy < CW_NVT; oy++) {
+			const int y = y0 + ry + oy;
+			if (y >= H || x >= W) continue;
+			float res;
+			if (valid_col) {
+				const int ty = ry + oy + R + 1;            // tile row of image row y
+				const uint32_t c = scomb[ty * CW_TX + cx];
+				const int U = (c >> 16) & 255, Dn = c >> 24;
+				const int hi = (ty + Dn - 1) * CW_TX + cx, lo = (ty - U) * CW_TX + cx;
+				res = (sS[hi] - sS[lo]) / (sN[hi] - sN[lo]);
+			} else {
+				res = __ldg(vol + (long)d * HW + (long)y * W + x);                 // :353-354 (keeps NaN)
+			}
+			out[(long)d * HW + (long)y * W + x] = res;
+		}
+	}
+	for (int dd = nproc; dd < dn; dd++) {              // tiles entirely inside the invalid triangle: plain copy
+		const int d = d0 + dd;
+		const float *plane = vol + (long)d * HW;
+#pragma unroll
+		for (int oy = 0; oy < CW_NVT; oy++) {
+			const int y = y0 + ry + oy;
+			if (y < H && x < W) out[(long)d * HW + (long)y * W + x] = __ldg(plane + (long)y * W + x);
+		}
+	}
+}
+
 // ------------------------------------------------------------------ cbca, shared-memory tile with run loops
 // (arms of 6..14 pixels, e.g. the Middlebury presets)
 constexpr int CB_TX = 64, CB_TY = 16, CB_DCH = 16, CB_NT = 256;
@@ -469,6 +646,26 @@ int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *
 }
 
 template <int R>
+int launch_o1(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int direction, cudaStream_t s)
+{
+	using Cfg = O1Cfg<R>;
+	static bool attr_done[64] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!attr_done[dev & 63]) {
+		ADC_CUDA(cudaFuncSetAttribute(cbca_o1_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+		attr_done[dev & 63] = true;
+	}
+	const char *env = getenv("ADCENSUS_CBCA_DCH");
+	int dch = env ? atoi(env) : 10;
+	if (dch < 1) dch = 1;
+	if (dch > CW_DCH_MAX) dch = CW_DCH_MAX;
+	dim3 grid(adc_div_up(W, CW_TX), adc_div_up(H, CW_TY), adc_div_up(D, dch));
+	cbca_o1_kernel<R><<<grid, CW_NT, Cfg::SMEM, s>>>(a0, a1, vol, out, D, H, W, direction, dch);
+	return 0;
+}
+
+template <int R>
 void launch_tile(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int direction, cudaStream_t s)
 {
 	dim3 grid(adc_div_up(W, CB_TX), adc_div_up(H, CB_TY), adc_div_up(D, CB_DCH));
@@ -498,6 +695,15 @@ int adc_cbca_packed(const uint32_t *pk, const float *x0c, const float *x1c,
 	const long HW = (long)H * W;
 	const uint32_t *a0 = pk, *a1 = pk + HW;
 	int halo = maxlen - 1;
+	if (fast == 2 && halo <= 13) {                     // experimental constant-work kernel (see cbca_o1_kernel)
+		int rc = halo <= 1 ? launch_o1<1>(a0, a1, vol, out, D, H, W, direction, s)
+			 : halo <= 4 ? launch_o1<4>(a0, a1, vol, out, D, H, W, direction, s)
+			 : halo <= 8 ? launch_o1<8>(a0, a1, vol, out, D, H, W, direction, s)
+				     : launch_o1<13>(a0, a1, vol, out, D, H, W, direction, s);
+		if (rc) return rc;
+		ADC_CHECK_LAUNCH();
+		return 0;
+	}
 	if (halo <= 1) {
 		int rc = fast ? launch_win<1, true>(a0, a1, vol, out, D, H, W, direction, s) : launch_win<1, false>(a0, a1, vol, out, D, H, W, direction, s);
 		if (rc) return rc;
@@ -550,6 +756,15 @@ extern "C" int mccnn_cbca_packed_fast(const void *packed, const float *x0c, cons
 	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1) || max_arm < 1) return ADCENSUS_EINVAL;
 	const uint32_t *pk = (const uint32_t *)packed;
 	return adc_cbca_packed(pk, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, adc_stream(stream), 1);
+}
+
+extern "C" int mccnn_cbca_packed_level(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+				       int D, int H, int W, int direction, int max_arm, int level, adcensus_stream_t stream)
+{
+	if (!packed || !x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
+	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1) || max_arm < 1 || level < 0 || level > 2) return ADCENSUS_EINVAL;
+	const uint32_t *pk = (const uint32_t *)packed;
+	return adc_cbca_packed(pk, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, adc_stream(stream), level);
 }
 
 extern "C" int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1, adcensus_stream_t stream)

@@ -34,7 +34,7 @@ struct mccnn_pipeline {
 	long HW, V;
 	size_t bytes;
 	int launches;
-	int fast_cbca;   // opt-in approximate CBCA (mccnn_pipeline_set_fast_cbca); 0 = exact (default)
+	int fast_cbca;   // opt-in approximate CBCA level (mccnn_pipeline_set_fast_cbca); 0 = exact (default)
 	// device buffers
 	float *vols;      // 2V: [0] left volume, [1] right volume (main.lua:946)
 	float *bufA;      // V : CBCA ping-pong / SGM transposed input
@@ -155,7 +155,8 @@ extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
 }
 
 extern "C" size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p) { return p ? p->bytes : 0; }
-extern "C" void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on) { if (p) p->fast_cbca = on ? 1 : 0; }
+// 0 exact (default), 1 per-row prefix sums, 2 experimental constant-work kernel (cbca_o1_kernel); other values -> 1
+extern "C" void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on) { if (p) p->fast_cbca = on == 2 ? 2 : (on ? 1 : 0); }
 static void overlap_release(mccnn_pipeline *p)
 {
 	const size_t f = sizeof(float);

@@ -181,7 +181,8 @@ class StereoPipeline:
     def set_fast_cbca(self, on=True):
         """Opt in to the approximate CBCA kernel (prefix sums per support row: ~1e-6 relative to the
         exact-order kernel, not bit-exact with the reference).  Default is exact."""
-        adcensus.lib().mccnn_pipeline_set_fast_cbca(self._h, int(bool(on)))
+        level = int(on) if isinstance(on, int) and not isinstance(on, bool) else int(bool(on))   # 2 = experimental kernel
+        adcensus.lib().mccnn_pipeline_set_fast_cbca(self._h, level)
 
     @property
     def device_bytes(self):

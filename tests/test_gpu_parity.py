@@ -457,6 +457,35 @@ def test_fast_cbca_mode_is_within_tolerance(oracle):
     sp.close()
 
 
+@pytest.mark.skipif(os.environ.get("MCCNN_EXPERIMENTAL") != "1",
+                    reason="experimental kernel (cbca level 2), not yet validated on hardware: set MCCNN_EXPERIMENTAL=1")
+@pytest.mark.parametrize("L1,tau1,direction", [(5, 0.13, -1), (5, 0.13, 1), (14, 0.02, -1), (2, 0.5, 1), (9, 5.0, -1)])
+def test_experimental_constant_work_cbca(oracle, L1, tau1, direction):
+    """cbca level 2 (prefix sums along x and y, oracle/cbca_prefix_model.py): within the 1e-4 bar, NaN pattern exact"""
+    import ctypes
+
+    H, W, C, D = 70, 300, 8, 36
+    p = synth.make_pair(H, W, C, D, seed=L1)
+    volL, volR = oracle.stereo_join(p["featL"], p["featR"], D)
+    vol = volL if direction == -1 else volR
+    x0c, x1c = oracle.cross(p["imgL"], L1, tau1), oracle.cross(p["imgR"], L1, tau1)
+    want = oracle.cbca(x0c, x1c, vol, direction)
+    lib = adcensus.lib()
+    lib.mccnn_packed_arms_bytes.restype = ctypes.c_size_t
+    a0, a1, v = cu(x0c)[None], cu(x1c)[None], cu(vol)[None]
+    packed = torch.empty(lib.mccnn_packed_arms_bytes(H, W), dtype=torch.uint8, device=dev())
+    out = torch.empty_like(v)
+    vp = lambda t_: ctypes.c_void_p(t_.data_ptr())
+    assert lib.mccnn_pack_arms(vp(a0), vp(a1), vp(packed), H, W, adcensus._stream(a0)) == 0
+    assert lib.mccnn_cbca_packed_level(vp(packed), vp(a0), vp(a1), vp(v), vp(out), D, H, W, direction, max(L1, 2), 2,
+                                       adcensus._stream(v)) == 0
+    g = out[0].cpu().numpy()
+    assert np.array_equal(np.isnan(g), np.isnan(want))
+    m = ~np.isnan(want)
+    err = np.abs(g[m] - want[m]) / np.maximum(1.0, np.abs(want[m]))
+    assert err.max() <= 1e-4, "max relative error %.3g" % err.max()
+
+
 def test_lua_face_through_the_reference_driver(oracle):
     """luaopen_libadcensus of OUR library (shim build), called by the very driver that calls the
     reference's: same 31 names, same positional signatures, same results."""
