@@ -494,7 +494,7 @@ cbca_o1_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1
 				const uint32_t c = scomb[ty * CW_TX + cx];
 				const int U = (c >> 16) & 255, Dn = c >> 24;
 				const int hi = (ty + Dn - 1) * CW_TX + cx, lo = (ty - U) * CW_TX + cx;
-				res = (sS[hi] - sS[lo]) / (sN[hi] - sN[lo]);
+				res = __fdividef(sS[hi] - sS[lo], sN[hi] - sN[lo]);   // count >= 1; 2-ulp division is inside the tolerance this kernel works to
 			} else {
 				res = __ldg(vol + (long)d * HW + (long)y * W + x);                 // :353-354 (keeps NaN)
 			}
