@@ -15,6 +15,7 @@ from mccnn_b200 import pipeline  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--fast", action="store_true")
+ap.add_argument("--fast-level", type=int, default=0, help="CBCA level: 1 = per-row prefix sums, 2 = experimental constant-work kernel")
 ap.add_argument("--D", type=int, default=228)
 ap.add_argument("--H", type=int, default=370)
 ap.add_argument("--W", type=int, default=1226)
@@ -28,8 +29,8 @@ fR = torch.nn.functional.normalize(torch.randn((a.C, a.H, a.W), device=dev, gene
 iL = torch.randn((a.H, a.W), device=dev, generator=g)
 iR = torch.randn((a.H, a.W), device=dev, generator=g)
 sp = pipeline.StereoPipeline(a.C, a.D, a.H, a.W, opt)
-if a.fast:
-    sp.set_fast_cbca(True)
+if a.fast or a.fast_level:
+    sp.set_fast_cbca(a.fast_level if a.fast_level else True)
 for _ in range(3):
     sp.run(fL, fR, iL, iR)
 torch.cuda.synchronize()
@@ -39,5 +40,6 @@ for _ in range(a.iters):
     sp.run(fL, fR, iL, iR)
 e1.record()
 torch.cuda.synchronize()
-print("dch=%s ms_per_pair=%.4f" % (os.environ.get("ADCENSUS_CBCA_DCH", "default"), e0.elapsed_time(e1) / a.iters))
+print("dch=%s cbca_level=%d ms_per_pair=%.4f" % (os.environ.get("ADCENSUS_CBCA_DCH", "default"),
+                                                  a.fast_level if a.fast_level else int(a.fast), e0.elapsed_time(e1) / a.iters))
 sp.close()
