@@ -13,7 +13,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous float32 (the reference
  *     ignores strides: raw THCudaTensor_data + sizes);
- *   - shapes: features (C,H,W); cost volumes (D,H,W); SGM volumes (H,W,D);
+ *   - shapes: features (C,H,W); cost volumes (D,H,W); SGM volumes (H,W,D); `*_pitched` / `*_dhw` entry points take
+ *     (D,H,ld) volumes with a row pitch ld (the fused pipeline's private layout);
  *     images / disparity maps (H,W); cross arms (4,H,W);
  *   - `stream` is a cudaStream_t (0 = legacy default stream, what the
  *     reference launches on); all work is asynchronous on it unless noted;
@@ -77,15 +78,15 @@ int mccnn_pack_arms(const float *x0c, const float *x1c, void *packed, int H, int
 int mccnn_cbca_packed(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 		      int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream);
 
-/* OPT-IN approximate aggregation, NOT bit-exact with the reference: every support row's run is summed
- * from per-row prefix sums and added as one value (same region, same row order, different rounding;
- * ~1e-6 relative, NaN positions identical; arms up to 5 pixels, longer arms fall back to the exact
- * kernels).  About 2.5x fewer instructions than the exact-order kernel, which is issue-bound. */
-/* level 0 / 1 / 2 as in mccnn_pipeline_set_fast_cbca */
-int mccnn_cbca_packed_level(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
-			    int D, int H, int W, int direction, int max_arm, int level, adcensus_stream_t stream);
-int mccnn_cbca_packed_fast(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
-			   int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream);
+/* Constant-work aggregation on PITCHED volumes (csrc/cbca_tma.cu): vol_in / vol_out are (D, H, ld) with a row pitch
+ * ld >= W, ld % 4 == 0 and 16-byte aligned bases, so that the plane tiles can be staged by TMA.  NOT bit-exact with
+ * the reference: every support row's run is a difference of row prefix sums and the rows are combined through
+ * running sums down the column (~45 instructions per output instead of ~200, ~1e-6 relative to the tap-by-tap
+ * sums, NaN positions identical); it serves the 1e-4 contract of the north star for float aggregation.  x0c / x1c
+ * must be cross() outputs with arms of at most max_arm <= 14 pixels, and the volume must be finite on its valid
+ * part (D <= W - border - 1 for a fix_border'ed volume).  The padding columns of vol_out are left untouched. */
+int mccnn_cbca_fast_pitched(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
+			    int D, int H, int W, int ld, int direction, int max_arm, adcensus_stream_t stream);
 
 /* adcensus.sgm2(x0, x1, input, output, tmp, pi1, pi2, tau_so, alpha1, sgm_q1,
  *               sgm_q2, direction)  adcensus.cu:535-697
@@ -95,6 +96,14 @@ int mccnn_cbca_packed_fast(const void *packed, const float *x0c, const float *x1
 int adcensus_sgm2(const float *x0, const float *x1, const float *input, float *output, float *tmp,
 		  int H, int W, int D, float pi1, float pi2, float tau_so, float alpha1,
 		  float sgm_q1, float sgm_q2, int direction, adcensus_stream_t stream);
+
+/* sgm2 on pitched (D, H, ld) volumes, no permutes (csrc/sgm_dhw.cu): output = sum of the four directional costs of
+ * input (right, left, down, up: the reference's accumulation order, bit-identical values), times 1/4 when div4 != 0
+ * (main.lua:1008-1020 in one call).  ld % 4 == 0, ld >= W rounded up to 4, 16-byte aligned bases; output need not be
+ * initialised and its padding columns receive unspecified values. */
+int mccnn_sgm2_dhw(const float *x0, const float *x1, const float *input, float *output,
+		   int H, int W, int ld, int D, float pi1, float pi2, float tau_so, float alpha1,
+		   float sgm_q1, float sgm_q2, int direction, int div4, adcensus_stream_t stream);
 
 /* Band-wise sgm2 for the row-band / column-band multi-GPU split: x0, x1 are the FULL Ht x Wt images,
  * input/output this GPU's band volume (H,W,D) at image offset (yoff, xoff); pass_mask selects scan
@@ -187,9 +196,12 @@ int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, int W,
 			  const mccnn_params *params, int device);
 void mccnn_pipeline_destroy(mccnn_pipeline *p);
 size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p);
-/* opt-in: approximate CBCA for the pipeline's iterations.  0 (default) = exact, bit-identical to the reference;
- * 1 = mccnn_cbca_packed_fast (per-row prefix sums, ~1e-6 relative); 2 = EXPERIMENTAL constant-work kernel (prefix sums
- * along x and y, mccnn_cbca_packed_level(..., 2)), not yet validated on hardware. */
+/* CBCA mode of the pipeline's iterations: 1 (default) = constant-work aggregation (mccnn_cbca_fast_pitched: volumes within
+ * the north star's 1e-4 of the reference, measured ~1e-6; disparity map identical except at isolated near-ties);
+ * 0 = exact, every output bit-identical to the reference.  ADCENSUS_CBCA_EXACT=1 in the environment makes 0 the default.
+ * mccnn_pipeline_set_fast_cbca is the older name of the same switch. */
+void mccnn_pipeline_set_cbca_mode(mccnn_pipeline *p, int mode);
+int mccnn_pipeline_get_cbca_mode(const mccnn_pipeline *p);
 void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on);
 /* opt-in: run the two directions of main.lua:955 concurrently (0 = off: one stream, 4V of volume buffers;
  * 1 = direction -1 on a side stream with its own 2V + tables, started when direction +1 reaches its SGM phase;

@@ -37,3 +37,44 @@ int adc_scratch_free(void *p, cudaStream_t s)
 }
 
 extern "C" const char *adcensus_version(void) { return "libadcensus_b200 0.1.0 (sm_100a)"; }
+
+// ---------------------------------------------------------------- TMA tensor maps
+#include "tma.cuh"
+
+typedef CUresult (*adc_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+					const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+					CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static adc_encode_tiled_fn adc_encode_tiled()
+{
+	static adc_encode_tiled_fn fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+		    q == cudaDriverEntryPointSuccess)
+			fn = (adc_encode_tiled_fn)p;
+		tried = true;
+	}
+	return fn;
+}
+
+int adc_tma_encode(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+		   const uint32_t *box)
+{
+	adc_encode_tiled_fn fn = adc_encode_tiled();
+	if (!fn) return (int)cudaErrorNotSupported;
+	if (rank < 2 || rank > 3 || ((uintptr_t)base & 15)) return ADCENSUS_EINVAL;
+	cuuint64_t gd[3], gs[2];
+	cuuint32_t bx[3], es[3] = {1, 1, 1};
+	for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; }
+	for (int i = 0; i + 1 < rank; i++) {
+		if (strides_bytes[i] % 16) return ADCENSUS_EINVAL;
+		gs[i] = strides_bytes[i];
+	}
+	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
+			CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+			CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}

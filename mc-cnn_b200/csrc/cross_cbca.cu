@@ -119,35 +119,29 @@ struct CWCfg {
 	static constexpr int TH = CW_TY + 2 * R;
 	static constexpr int TWP = CW_TX + 2 * R + 1;               // odd pitch: conflict-free column walks
 	static constexpr int A1W = CW_TX + CW_DCH_MAX;             // right-image arm window for up to CW_DCH_MAX disparities
-	// plane-tile buffers: 2 for the exact kernel (double-buffered), 1 for FAST
-	static constexpr int PW = TWP + 1;                          // prefix row: P[c] = sum of columns < c
+	// two plane-tile buffers (double-buffered)
 	static constexpr int SMEM = (TH * CW_TX + TH * A1W + TH * CW_TX + 2 * TH * TWP) * 4;
-	static constexpr int SMEM_FAST = (TH * CW_TX + TH * A1W + TH * CW_TX + TH * TWP + TH * PW) * 4;
 };
 
-// FAST (opt-in, NOT bit-exact): each row's run is summed as a difference of per-row prefix sums
-// (built in double, stored in fp32) and added to the output as ONE value, i.e. acc += round(sum of
-// run) instead of acc = (((acc + v1) + v2) + ...).  Same region, same row order, different rounding:
-// volumes agree with the exact mode to ~1e-6 relative (bar: 1e-4).
-template <int R, bool FAST>
+// vol / out: (D, H, ld) with row pitch ld >= W (ld == W for the API-facing contiguous tensors)
+template <int R>
 __global__ void __launch_bounds__(CW_NT, 2)
 cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
-		const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction, int dch)
+		const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int ld, int direction, int dch)
 {
 	using Cfg = CWCfg<R>;
-	constexpr int TH = Cfg::TH, TWP = Cfg::TWP, A1W = Cfg::A1W, PW = Cfg::PW;
+	constexpr int TH = Cfg::TH, TWP = Cfg::TWP, A1W = Cfg::A1W;
 	extern __shared__ __align__(16) uint32_t cw_smem[];
 	uint32_t *sa0 = cw_smem;                       // [TH][CW_TX]  left-image packed arms (L | R<<8 | U<<16 | D<<24) of the tile
 	uint32_t *sa1 = sa0 + TH * CW_TX;              // [TH][A1W]    right-image packed arms, shifted window
 	uint32_t *scomb = sa1 + TH * A1W;              // [TH][CW_TX]  byte-wise minimum of both for the current d
-	float *svbuf = reinterpret_cast<float *>(scomb + TH * CW_TX);  // NBUF x [TH][TWP] volume plane tile + halo
-	float *sp = svbuf + (FAST ? 1 : 2) * TH * TWP;                // [TH][PW]  FAST only: row prefix sums
+	float *svbuf = reinterpret_cast<float *>(scomb + TH * CW_TX);  // 2 x [TH][TWP] volume plane tile + halo
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int x0 = blockIdx.x * CW_TX, y0 = blockIdx.y * CW_TY, d0 = blockIdx.z * dch;   // dch <= CW_DCH_MAX disparities per CTA
 	const int dn = min(dch, D - d0);
 	const int a1x0 = direction > 0 ? x0 + d0 : x0 - (d0 + dch - 1);
-	const long HW = (long)H * W;
+	const long HW = (long)H * ld;                  // elements per plane
 
 	const int cx = 32 * (warp & 3) + lane;         // this thread's tile column
 	const int ry = CW_NVT * (warp >> 2);           // first of its NVT output rows (tile-relative)
@@ -182,7 +176,7 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 		for (int r = warp; r < TH; r += NW) {
 			const int yy = y0 - R + r;
 			const bool rowok = yy >= 0 && yy < H;
-			const float *grow = plane + (long)(rowok ? yy : 0) * W;
+			const float *grow = plane + (long)(rowok ? yy : 0) * ld;
 #pragma unroll
 			for (int m = 0; m < (TWP + 31) / 32; m++) {
 				const int c = lane + 32 * m, xx = x0 - R + c;
@@ -195,9 +189,9 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 			}
 		}
 	};
-	// PD = 1 (exact kernel): the tile of disparity dd+1 streams into the other buffer while dd is aggregated
-	constexpr int PD = FAST ? 0 : 1;
-	if (PD == 1 && nproc > 0) {
+	// the tile of disparity dd+1 streams into the other buffer while dd is aggregated
+	constexpr int PD = 1;
+	if (nproc > 0) {
 		issue_tile(d0, svbuf);
 		asm volatile("cp.async.commit_group;");
 	}
@@ -224,37 +218,6 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 		}
 		asm volatile("cp.async.wait_group %0;" ::"n"(PD));
 		__syncthreads();
-		if constexpr (FAST) {
-			// exclusive prefix sums of every tile row, accumulated in double, rounded once per entry
-			constexpr int EPL = (TWP + 31) / 32;               // elements per lane
-			for (int r = warp; r < TH; r += NW) {
-				double loc[EPL];
-				double run = 0.0;
-#pragma unroll
-				for (int i = 0; i < EPL; i++) {
-					const int c = lane * EPL + i;
-					float v = c < TWP ? sv[r * TWP + c] : 0.0f;
-					v = v == v ? v : 0.0f;                     // NaN = invalid triangle, never inside a run
-					run += (double)v;
-					loc[i] = run;
-				}
-				double incl = run;                             // inclusive scan of the lane totals
-#pragma unroll
-				for (int o = 1; o < 32; o <<= 1) {
-					const double up = __shfl_up_sync(0xffffffffu, incl, o);
-					if (lane >= o) incl += up;
-				}
-				const double base = incl - run;
-#pragma unroll
-				for (int i = 0; i < EPL; i++) {
-					const int c = lane * EPL + i;
-					if (c < TWP) sp[r * PW + c + 1] = (float)(base + loc[i]);
-				}
-				if (lane == 0) sp[r * PW] = 0.0f;
-			}
-			__syncthreads();
-		}
-
 		// Outputs are accumulated in PAIRS (rows 2j, 2j+1) with the packed FFMA2 of sm_100a
 		// (fma.rn.f32x2: two independent IEEE fmas per instruction): {acc[2j], acc[2j+1]} +=
 		// {q[2j], q[2j+1]} * wm[k].  A row touches 2R+1 outputs = R+1 pairs, so a slot costs R+1
@@ -278,20 +241,12 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 			const float LRf = (float)(L + Rr - 1);             // taps of this row's run (:364-369), exact in fp32
 			const unsigned long long LR2 = adc_pack2(LRf, LRf);
 			unsigned long long wm2[2 * R + 1];
-			unsigned long long S2 = 0;
-			if constexpr (FAST) {
-				// sum of the run (x - L, x + Rr): tile columns [cx + R - L + 1, cx + R + Rr)
-				const float *prow = sp + (ry + ri) * PW + cx + R;
-				const float S = prow[Rr] - prow[1 - L];
-				S2 = adc_pack2(S, S);
-			} else {
 #pragma unroll
-				for (int k = 0; k <= 2 * R; k++) {
-					// slot inside the run (x - L, x + Rr) (:362-364) keeps its value, the others become +0.0f
-					const float v = wrow[k];
-					const float w = k < R ? (L > R - k ? v : 0.0f) : (k > R ? (Rr > k - R ? v : 0.0f) : (L > 0 ? v : 0.0f));
-					wm2[k] = adc_pack2(w, w);
-				}
+			for (int k = 0; k <= 2 * R; k++) {
+				// slot inside the run (x - L, x + Rr) (:362-364) keeps its value, the others become +0.0f
+				const float v = wrow[k];
+				const float w = k < R ? (L > R - k ? v : 0.0f) : (k > R ? (Rr > k - R ? v : 0.0f) : (L > 0 ? v : 0.0f));
+				wm2[k] = adc_pack2(w, w);
 			}
 #pragma unroll
 			for (int j = 0; j < CW_NVT / 2; j++) {
@@ -303,12 +258,8 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 				const float qlo = inlo && (dlo < 0 ? U[2 * j] > -dlo : Dn[2 * j] > dlo) ? 1.0f : 0.0f;
 				const float qhi = inhi && (dhi < 0 ? U[2 * j + 1] > -dhi : Dn[2 * j + 1] > dhi) ? 1.0f : 0.0f;
 				const unsigned long long q2 = adc_pack2(qlo, qhi);
-				if constexpr (FAST) {
-					acc2[j] = adc_fma2(q2, S2, acc2[j]);
-				} else {
 #pragma unroll
-					for (int k = 0; k <= 2 * R; k++) acc2[j] = adc_fma2(q2, wm2[k], acc2[j]);   // :364-367
-				}
+				for (int k = 0; k <= 2 * R; k++) acc2[j] = adc_fma2(q2, wm2[k], acc2[j]);   // :364-367
 				cnt2[j] = adc_fma2(q2, LR2, cnt2[j]);                                          // :368
 			}
 		}
@@ -321,7 +272,7 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 			adc_unpack2(cnt2[oy / 2], clo, chi);
 			float res = valid_col ? ((oy & 1) ? ahi / chi : alo / clo)                     // :373
 					      : sv[(ry + oy + R) * TWP + cx + R];                      // :353-354 (keeps NaN)
-			out[(long)d * HW + (long)y * W + x] = res;
+			out[(long)d * HW + (long)y * ld + x] = res;
 		}
 	}
 	for (int dd = nproc; dd < dn; dd++) {              // tiles entirely inside the invalid triangle
@@ -330,184 +281,7 @@ cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a
 #pragma unroll
 		for (int oy = 0; oy < CW_NVT; oy++) {
 			const int y = y0 + ry + oy;
-			if (y < H && x < W) out[(long)d * HW + (long)y * W + x] = __ldg(plane + (long)y * W + x);
-		}
-	}
-}
-
-// ------------------------------------------------------------------ cbca, constant work per pixel (opt-in level 2)
-// EXPERIMENTAL until validated on the GPU (mccnn_pipeline_set_fast_cbca(p, 2) / fast == 2): NOT bit-exact by
-// construction, aimed at the north star's 1e-4 bar for float aggregation.  Numerical model and CPU tests:
-// oracle/cbca_prefix_model.py, tests/test_cbca_prefix_model.py (2.5e-6 relative after four iterations).
-//
-// The run of a support row depends on (d, row, column) only, not on which output row uses it:
-//     S(r, x) = I(r, x + R_ - 1) - I(r, x - L)           I = inclusive prefix of the tile row (NaN -> 0)
-//     out(y, x) = (T(y + D - 1, x) - T(y - U, x)) / (N(y + D - 1, x) - N(y - U, x))
-// with T, N the inclusive prefixes of S and of the run lengths along the rows.  All prefixes are local to the
-// 32 x 128 tile (+ halo), which bounds the cancellation error.  Per plane: combined arms straight from the
-// (L2-resident) packed arm images, row scan in place on the double-buffered plane tile, run sums, column scan
-// (run sums on warps 0-3, run lengths on warps 4-7), outputs: ~75 instructions per output, five barriers.
-template <int R>
-struct O1Cfg {
-	// An arm LENGTH is the distance to the first EXCLUDED pixel, so lengths reach R + 1 while the support only
-	// reaches R pixels out.  The prefix differences index that excluded pixel (I(x - L), T(y - U)): the tile
-	// therefore carries one extra row above and one extra column to the left of the R-pixel halo.
-	static constexpr int TH = CW_TY + 2 * R + 1;   // image rows y0 - R - 1 .. y0 + CW_TY + R - 1
-	static constexpr int TWP = CW_TX + 2 * R + 1;  // image columns x0 - R - 1 .. x0 + CW_TX + R - 1 (odd pitch)
-	static constexpr int SMEM = (TH * CW_TX + 2 * TH * TWP + 2 * TH * CW_TX) * 4;
-};
-
-template <int R>
-__global__ void __launch_bounds__(CW_NT, (O1Cfg<R>::SMEM <= 110 * 1024) ? 2 : 1)
-cbca_o1_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
-	       const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction, int dch)
-{
-	using Cfg = O1Cfg<R>;
-	constexpr int TH = Cfg::TH, TWP = Cfg::TWP;
-	extern __shared__ __align__(16) uint32_t cw_smem[];
-	uint32_t *scomb = cw_smem;                                     // [TH][CW_TX] combined arms of the current d
-	float *svbuf = reinterpret_cast<float *>(scomb + TH * CW_TX);  // 2 x [TH][TWP] plane tile + halo, scanned in place
-	float *sS = svbuf + 2 * TH * TWP;                              // [TH][CW_TX] run sums, then their prefix along rows
-	float *sN = sS + TH * CW_TX;                                   // [TH][CW_TX] run lengths, then their prefix
-
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int x0 = blockIdx.x * CW_TX, y0 = blockIdx.y * CW_TY, d0 = blockIdx.z * dch;
-	const int dn = min(dch, D - d0);
-	const long HW = (long)H * W;
-	const int cx = 32 * (warp & 3) + lane;
-	const int ry = CW_NVT * (warp >> 2);
-	const int x = x0 + cx;
-	constexpr int NW = CW_NT / 32;
-
-	int nproc = 0;   // disparities whose tile is not entirely inside the invalid triangle (a prefix of the chunk)
-	while (nproc < dn && !(direction < 0 ? (x0 + CW_TX - 1 - (d0 + nproc) < 0) : (x0 + d0 + nproc >= W))) nproc++;
-
-	auto issue_tile = [&](int d, float *buf) {
-		const float *plane = vol + (long)d * HW;
-		for (int r = warp; r < TH; r += NW) {
-			const int yy = y0 - R - 1 + r;
-			const bool rowok = yy >= 0 && yy < H;
-			const float *grow = plane + (long)(rowok ? yy : 0) * W;
-#pragma unroll
-			for (int m = 0; m < (TWP + 31) / 32; m++) {
-				const int c = lane + 32 * m, xx = x0 - R - 1 + c;
-				if (c < TWP) {
-					const bool ok = rowok && xx >= 0 && xx < W;
-					const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + r * TWP + c);
-					const int nbytes = ok ? 4 : 0;
-					asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(grow + (ok ? xx : 0)), "r"(nbytes));
-				}
-			}
-		}
-	};
-	if (nproc > 0) {
-		issue_tile(d0, svbuf);
-		asm volatile("cp.async.commit_group;");
-	}
-	for (int dd = 0; dd < nproc; dd++) {
-		const int d = d0 + dd;
-		const int sh = d * direction;
-		const int xs = x + sh;
-		const bool valid_col = x < W && xs >= 0 && xs < W;
-		float *sv = svbuf + (dd & 1) * TH * TWP;
-		__syncthreads();                               // every reader of the previous plane's arrays is done
-		if (dd + 1 < nproc) issue_tile(d + 1, svbuf + ((dd + 1) & 1) * TH * TWP);
-		asm volatile("cp.async.commit_group;");
-		// combined arms: byte-wise min of the left arms at x and the right arms at x + d*dir (0 outside the image)
-		for (int r = warp; r < TH; r += NW) {
-			const int yy = y0 - R - 1 + r;
-			const bool rowok = yy >= 0 && yy < H;
-#pragma unroll
-			for (int m = 0; m < CW_TX / 32; m++) {
-				const int c = lane + 32 * m, xx = x0 + c, xr = xx + sh;
-				const uint32_t a = (rowok && xx < W) ? __ldg(a0g + (long)yy * W + xx) : 0u;
-				const uint32_t b = (rowok && xr >= 0 && xr < W) ? __ldg(a1g + (long)yy * W + xr) : 0u;
-				scomb[r * CW_TX + c] = __vminu4(a, b);
-			}
-		}
-		asm volatile("cp.async.wait_group 1;");        // the tile of d has landed (d + 1 may still be in flight)
-		__syncthreads();
-
-		// 1. inclusive prefix of every tile row, in place; NaN (invalid triangle, never inside a run) counts as 0
-		constexpr int EPL = (TWP + 31) / 32;
-		for (int r = warp; r < TH; r += NW) {
-			float loc[EPL];
-			float run = 0.0f;
-#pragma unroll
-			for (int i = 0; i < EPL; i++) {
-				const int c = lane * EPL + i;
-				float v = c < TWP ? sv[r * TWP + c] : 0.0f;
-				v = v == v ? v : 0.0f;
-				run += v;
-				loc[i] = run;
-			}
-			float incl = run;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const float up = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= o) incl += up;
-			}
-			const float base = incl - run;
-#pragma unroll
-			for (int i = 0; i < EPL; i++) {
-				const int c = lane * EPL + i;
-				if (c < TWP) sv[r * TWP + c] = base + loc[i];
-			}
-		}
-		__syncthreads();
-
-		// 2. sum and length of the run (x - L, x + R_) of every tile row at this thread's column (:362-369)
-		for (int r = warp >> 2; r < TH; r += 2) {
-			const uint32_t c = scomb[r * CW_TX + cx];
-			const int L = c & 255, Rr = (c >> 8) & 255;
-			const float *I = sv + r * TWP + cx + R + 1;   // I[k]: inclusive prefix at image column x + k (k >= -R - 1)
-			float S = 0.0f, C = 0.0f;
-			if (L > 0) {                               // 0 = pixel outside either image
-				S = I[Rr - 1] - I[-L];
-				C = (float)(L + Rr - 1);
-			}
-			sS[r * CW_TX + cx] = S;
-			sN[r * CW_TX + cx] = C;
-		}
-		__syncthreads();
-
-		// 3. inclusive prefixes along the rows: run sums on warps 0-3, run lengths on warps 4-7
-		{
-			float *col = (warp < 4 ? sS : sN) + cx;
-			float run = 0.0f;
-#pragma unroll 8
-			for (int r = 0; r < TH; r++) {
-				run += col[r * CW_TX];
-				col[r * CW_TX] = run;
-			}
-		}
-		__syncthreads();
-
-		// 4. outputs: rows y - U + 1 .. y + Dn - 1 of the column (:359-361, :373)
-#pragma unroll
-		for (int oy = 0; oy < CW_NVT; oy++) {
-			const int y = y0 + ry + oy;
-			if (y >= H || x >= W) continue;
-			float res;
-			if (valid_col) {
-				const int ty = ry + oy + R + 1;            // tile row of image row y
-				const uint32_t c = scomb[ty * CW_TX + cx];
-				const int U = (c >> 16) & 255, Dn = c >> 24;
-				const int hi = (ty + Dn - 1) * CW_TX + cx, lo = (ty - U) * CW_TX + cx;
-				res = __fdividef(sS[hi] - sS[lo], sN[hi] - sN[lo]);   // count >= 1; 2-ulp division is inside the tolerance this kernel works to
-			} else {
-				res = __ldg(vol + (long)d * HW + (long)y * W + x);                 // :353-354 (keeps NaN)
-			}
-			out[(long)d * HW + (long)y * W + x] = res;
-		}
-	}
-	for (int dd = nproc; dd < dn; dd++) {              // tiles entirely inside the invalid triangle: plain copy
-		const int d = d0 + dd;
-		const float *plane = vol + (long)d * HW;
-#pragma unroll
-		for (int oy = 0; oy < CW_NVT; oy++) {
-			const int y = y0 + ry + oy;
-			if (y < H && x < W) out[(long)d * HW + (long)y * W + x] = __ldg(plane + (long)y * W + x);
+			if (y < H && x < W) out[(long)d * HW + (long)y * ld + x] = __ldg(plane + (long)y * ld + x);
 		}
 	}
 }
@@ -519,7 +293,7 @@ constexpr int CB_TX = 64, CB_TY = 16, CB_DCH = 16, CB_NT = 256;
 template <int R>  // halo = longest arm - 1
 __global__ void __launch_bounds__(CB_NT)
 cbca_loop_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
-		 const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int direction)
+		 const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int ld, int direction)
 {
 	constexpr int TH = CB_TY + 2 * R;          // tile rows incl. halo
 	constexpr int TW = CB_TX + 2 * R;          // volume tile columns incl. halo
@@ -549,7 +323,7 @@ cbca_loop_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ 
 	const int lx = tid % CB_TX;                // 0..63
 	const int ly = tid / CB_TX;                // 0..3 ; rows ly, ly+4, ly+8, ly+12
 	const int x = x0 + lx;
-	const long HW = (long)H * W;
+	const long HW = (long)H * ld;              // elements per plane
 
 	for (int dd = 0; dd < dn; dd++) {
 		const int d = d0 + dd;
@@ -558,7 +332,7 @@ cbca_loop_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ 
 		for (int i = tid; i < TH * TW; i += CB_NT) {
 			int r = i / TW, c = i % TW;
 			int yy = y0 - R + r, xx = x0 - R + c;
-			sv[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(plane + (long)yy * W + xx) : 0.0f;
+			sv[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(plane + (long)yy * ld + xx) : 0.0f;
 		}
 		__syncthreads();
 		const int xs = x + d * direction;
@@ -586,7 +360,7 @@ cbca_loop_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ 
 				}
 				res = sum / (float)cnt;                                    // :373
 			}
-			out[(long)d * HW + (long)y * W + x] = res;
+			out[(long)d * HW + (long)y * ld + x] = res;
 		}
 	}
 }
@@ -596,7 +370,7 @@ cbca_loop_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ 
 // largest shared-memory halo or the arms are not integer cross() outputs.
 __global__ void cbca_generic_kernel(const float *__restrict__ x0c, const float *__restrict__ x1c,
 				    const float *__restrict__ vol, float *__restrict__ out,
-				    long size, int H, int W, int direction)
+				    long size, int H, int W, int ld, int direction)
 {
 	long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (id >= size) return;
@@ -605,7 +379,8 @@ __global__ void cbca_generic_kernel(const float *__restrict__ x0c, const float *
 	int y = (int)((id / W) % H);
 	int d = (int)(id / HW);
 	int xs = x + d * direction;
-	if (xs < 0 || xs >= W) { out[id] = vol[id]; return; }
+	const long prow = ((long)d * H) * ld;      // plane offset in the (D, H, ld) volumes
+	if (xs < 0 || xs >= W) { out[prow + (long)y * ld + x] = vol[prow + (long)y * ld + x]; return; }
 	float sum = 0.0f;
 	int cnt = 0;
 	int yy_s = (int)fmaxf(x0c[2 * HW + (long)y * W + x], x1c[2 * HW + (long)y * W + xs]);
@@ -614,23 +389,23 @@ __global__ void cbca_generic_kernel(const float *__restrict__ x0c, const float *
 		int xx_s = (int)fmaxf(x0c[(long)yy * W + x], x1c[(long)yy * W + xs] - d * direction);
 		int xx_t = (int)fminf(x0c[HW + (long)yy * W + x], x1c[HW + (long)yy * W + xs] - d * direction);
 		for (int xx = xx_s + 1; xx < xx_t; xx++) {
-			sum += __ldg(vol + (long)d * HW + (long)yy * W + xx);
+			sum += __ldg(vol + prow + (long)yy * ld + xx);
 			cnt++;
 		}
 	}
-	out[id] = sum / (float)cnt;
+	out[prow + (long)y * ld + x] = sum / (float)cnt;
 }
 
-template <int R, bool FAST>
-int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int direction, cudaStream_t s)
+template <int R>
+int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int ld, int direction, cudaStream_t s)
 {
 	using Cfg = CWCfg<R>;
-	constexpr int SMEM = FAST ? Cfg::SMEM_FAST : Cfg::SMEM;
+	constexpr int SMEM = Cfg::SMEM;
 	static bool attr_done[64] = {false};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!attr_done[dev & 63]) {
-		ADC_CUDA(cudaFuncSetAttribute(cbca_win_kernel<R, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+		ADC_CUDA(cudaFuncSetAttribute(cbca_win_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
 		attr_done[dev & 63] = true;
 	}
 	// disparities per CTA.  Measured at 370x1226x228: 4..12 -> 1.01-1.04 ms, 16 -> 1.01 ms, 19 (whole
@@ -641,35 +416,15 @@ int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *
 	if (dch < 1) dch = 1;
 	if (dch > CW_DCH_MAX) dch = CW_DCH_MAX;
 	dim3 grid(adc_div_up(W, CW_TX), adc_div_up(H, CW_TY), adc_div_up(D, dch));
-	cbca_win_kernel<R, FAST><<<grid, CW_NT, SMEM, s>>>(a0, a1, vol, out, D, H, W, direction, dch);
+	cbca_win_kernel<R><<<grid, CW_NT, SMEM, s>>>(a0, a1, vol, out, D, H, W, ld, direction, dch);
 	return 0;
 }
 
 template <int R>
-int launch_o1(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int direction, cudaStream_t s)
-{
-	using Cfg = O1Cfg<R>;
-	static bool attr_done[64] = {false};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (!attr_done[dev & 63]) {
-		ADC_CUDA(cudaFuncSetAttribute(cbca_o1_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-		attr_done[dev & 63] = true;
-	}
-	const char *env = getenv("ADCENSUS_CBCA_DCH");
-	int dch = env ? atoi(env) : 10;
-	if (dch < 1) dch = 1;
-	if (dch > CW_DCH_MAX) dch = CW_DCH_MAX;
-	dim3 grid(adc_div_up(W, CW_TX), adc_div_up(H, CW_TY), adc_div_up(D, dch));
-	cbca_o1_kernel<R><<<grid, CW_NT, Cfg::SMEM, s>>>(a0, a1, vol, out, D, H, W, direction, dch);
-	return 0;
-}
-
-template <int R>
-void launch_tile(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int direction, cudaStream_t s)
+void launch_tile(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int ld, int direction, cudaStream_t s)
 {
 	dim3 grid(adc_div_up(W, CB_TX), adc_div_up(H, CB_TY), adc_div_up(D, CB_DCH));
-	cbca_loop_kernel<R><<<grid, CB_NT, 0, s>>>(a0, a1, vol, out, D, H, W, direction);
+	cbca_loop_kernel<R><<<grid, CB_NT, 0, s>>>(a0, a1, vol, out, D, H, W, ld, direction);
 }
 
 }  // namespace
@@ -686,36 +441,26 @@ int adc_pack_arms(const float *xc, uint32_t *pk, int which, int H, int W, int *m
 	return 0;
 }
 
-// maxlen = longest arm (distance to the exclusive end-point) of either image
-// fast != 0 selects the prefix-sum kernel where one exists (arms up to 5 pixels); longer arms always
-// take the exact kernels
+// Exact (bit-identical) aggregation.  maxlen = longest arm (distance to the exclusive end-point) of either
+// image; vol / out are (D, H, ld) with ld >= W (ld == W: the API-facing contiguous tensors).
 int adc_cbca_packed(const uint32_t *pk, const float *x0c, const float *x1c,
-		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s, int fast)
+		    const float *vol, float *out, int D, int H, int W, int ld, int direction, int maxlen, cudaStream_t s)
 {
 	const long HW = (long)H * W;
 	const uint32_t *a0 = pk, *a1 = pk + HW;
 	int halo = maxlen - 1;
-	if (fast == 2 && halo <= 13) {                     // experimental constant-work kernel (see cbca_o1_kernel)
-		int rc = halo <= 1 ? launch_o1<1>(a0, a1, vol, out, D, H, W, direction, s)
-			 : halo <= 4 ? launch_o1<4>(a0, a1, vol, out, D, H, W, direction, s)
-			 : halo <= 8 ? launch_o1<8>(a0, a1, vol, out, D, H, W, direction, s)
-				     : launch_o1<13>(a0, a1, vol, out, D, H, W, direction, s);
-		if (rc) return rc;
-		ADC_CHECK_LAUNCH();
-		return 0;
-	}
 	if (halo <= 1) {
-		int rc = fast ? launch_win<1, true>(a0, a1, vol, out, D, H, W, direction, s) : launch_win<1, false>(a0, a1, vol, out, D, H, W, direction, s);
+		int rc = launch_win<1>(a0, a1, vol, out, D, H, W, ld, direction, s);
 		if (rc) return rc;
 	} else if (halo <= 4) {
-		int rc = fast ? launch_win<4, true>(a0, a1, vol, out, D, H, W, direction, s) : launch_win<4, false>(a0, a1, vol, out, D, H, W, direction, s);
+		int rc = launch_win<4>(a0, a1, vol, out, D, H, W, ld, direction, s);
 		if (rc) return rc;
 	}
-	else if (halo <= 8) launch_tile<8>(a0, a1, vol, out, D, H, W, direction, s);
-	else if (halo <= 13) launch_tile<13>(a0, a1, vol, out, D, H, W, direction, s);
+	else if (halo <= 8) launch_tile<8>(a0, a1, vol, out, D, H, W, ld, direction, s);
+	else if (halo <= 13) launch_tile<13>(a0, a1, vol, out, D, H, W, ld, direction, s);
 	else {
 		long size = (long)D * H * W;
-		cbca_generic_kernel<<<adc_div_up(size, 256), 256, 0, s>>>(x0c, x1c, vol, out, size, H, W, direction);
+		cbca_generic_kernel<<<adc_div_up(size, 256), 256, 0, s>>>(x0c, x1c, vol, out, size, H, W, ld, direction);
 	}
 	ADC_CHECK_LAUNCH();
 	return 0;
@@ -744,27 +489,7 @@ extern "C" int mccnn_cbca_packed(const void *packed, const float *x0c, const flo
 	if (!packed || !x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
 	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1) || max_arm < 1) return ADCENSUS_EINVAL;
 	const uint32_t *pk = (const uint32_t *)packed;
-	return adc_cbca_packed(pk, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, adc_stream(stream), 0);
-}
-
-// Opt-in approximate aggregation (prefix sums per support row; same region and row order, different
-// rounding: ~1e-6 relative to the exact kernel, NaN positions identical).  Not bit-exact with the reference.
-extern "C" int mccnn_cbca_packed_fast(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
-				      int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream)
-{
-	if (!packed || !x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
-	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1) || max_arm < 1) return ADCENSUS_EINVAL;
-	const uint32_t *pk = (const uint32_t *)packed;
-	return adc_cbca_packed(pk, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, adc_stream(stream), 1);
-}
-
-extern "C" int mccnn_cbca_packed_level(const void *packed, const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
-				       int D, int H, int W, int direction, int max_arm, int level, adcensus_stream_t stream)
-{
-	if (!packed || !x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
-	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1) || max_arm < 1 || level < 0 || level > 2) return ADCENSUS_EINVAL;
-	const uint32_t *pk = (const uint32_t *)packed;
-	return adc_cbca_packed(pk, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, adc_stream(stream), level);
+	return adc_cbca_packed(pk, x0c, x1c, vol_in, vol_out, D, H, W, W, direction, max_arm, adc_stream(stream));
 }
 
 extern "C" int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1, adcensus_stream_t stream)
@@ -790,7 +515,7 @@ extern "C" int adcensus_cbca_ex(const float *x0c, const float *x1c, const float 
 	rc = (int)cudaMemsetAsync(maxlen_dev, 0, sizeof(int), s);
 	if (!rc) rc = adc_pack_arms(x0c, packed, 0, H, W, maxlen_dev, s);
 	if (!rc) rc = adc_pack_arms(x1c, packed, 1, H, W, maxlen_dev, s);
-	if (!rc) rc = adc_cbca_packed(packed, x0c, x1c, vol_in, vol_out, D, H, W, direction, max_arm, s, 0);
+	if (!rc) rc = adc_cbca_packed(packed, x0c, x1c, vol_in, vol_out, D, H, W, W, direction, max_arm, s);
 	int rc2 = adc_scratch_free(packed, s);
 	return rc ? rc : rc2;
 }
@@ -812,7 +537,7 @@ extern "C" int adcensus_cbca(const float *x0c, const float *x1c, const float *vo
 	if (!rc) rc = adc_pack_arms(x1c, packed, 1, H, W, maxlen_dev, s);
 	if (!rc) rc = (int)cudaMemcpyAsync(&maxlen, maxlen_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
 	if (!rc) rc = (int)cudaStreamSynchronize(s);
-	if (!rc) rc = adc_cbca_packed(packed, x0c, x1c, vol_in, vol_out, D, H, W, direction, maxlen, s, 0);
+	if (!rc) rc = adc_cbca_packed(packed, x0c, x1c, vol_in, vol_out, D, H, W, W, direction, maxlen, s);
 	int rc2 = adc_scratch_free(packed, s);
 	return rc ? rc : rc2;
 }

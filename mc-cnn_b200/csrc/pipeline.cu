@@ -17,40 +17,59 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 // internal entry points of the other translation units
 size_t adc_packed_words(int H, int W);
 int adc_pack_arms(const float *xc, uint32_t *pk, int which, int H, int W, int *maxlen_dev, cudaStream_t s);
 int adc_cbca_packed(const uint32_t *pk, const float *x0c, const float *x1c,
-		    const float *vol, float *out, int D, int H, int W, int direction, int maxlen, cudaStream_t s, int fast);
-size_t adc_sgm_table_bytes(int H, int W, int D);
-int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, uint8_t *tab, int H, int W, int D,
-	     float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
-	     bool zero_out, cudaStream_t s);
+		    const float *vol, float *out, int D, int H, int W, int ld, int direction, int maxlen, cudaStream_t s);
+size_t adc_packed_hv_words(int H, int W);
+int adc_pack_arms_hv(const float *xc, uint32_t *hv, int which, int H, int W, cudaStream_t s);
+int adc_cbca_tma_max_halo();
+void adc_cbca_tma_box(int halo, int *box_w, int *box_h);
+int adc_cbca_tma(const CUtensorMap *tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
+		 int halo, cudaStream_t s);
+size_t adc_sgm_dhw_table_bytes(int H, int W, int D);
+int adc_sgm2_dhw(const float *x0, const float *x1, const float *in, float *acc, uint8_t *tab, int H, int W, int ld, int D,
+		 float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction, bool div4, cudaStream_t s);
+int adc_stereo_join(const float *input_L, const float *input_R, float *output_L, float *output_R,
+		    int C, int D, int H, int W, int ldo, cudaStream_t s);
+int adc_fill_invalid(float *volL, float *volR, int D, int H, int W, int ld, cudaStream_t s);
+int adc_fix_border(float *vol, int D, int H, int W, int ld, int n, int direction, cudaStream_t s);
+int adc_argmin_pitched(const float *vol, float *disp, int D, int H, int W, int ld, cudaStream_t s);
+int adc_subpixel(const float *d0, const float *c2, float *out, int H, int W, int ld, int disp_max, cudaStream_t s);
 
+// Private volume layout: (D, H, ld), ld = W rounded up to a multiple of 4 floats.  Every row then starts on a
+// 16-byte boundary: tensor maps (TMA) can describe the volumes, and 16-byte vector / cp.async accesses along x are
+// legal everywhere (the API-facing (D,H,W) tensors with W = 1226 are only 8-byte aligned per row).  The padding
+// columns hold unspecified values and are never read as data.
 struct mccnn_pipeline {
-	int C, D, H, W, device;
+	int C, D, H, W, ld, device;
 	mccnn_params prm;
-	long HW, V;
+	long HW, V;       // H*W; elements of one private volume = D*H*ld
 	size_t bytes;
 	int launches;
-	int fast_cbca;   // opt-in approximate CBCA level (mccnn_pipeline_set_fast_cbca); 0 = exact (default)
+	int cbca_mode;    // 1 = constant-work aggregation (default, 1e-4 contract), 0 = exact (bit-identical to the reference)
 	// device buffers
 	float *vols;      // 2V: [0] left volume, [1] right volume (main.lua:946)
-	float *bufA;      // V : CBCA ping-pong / SGM transposed input
-	float *bufC;      // V : SGM accumulator (H,W,D)
+	float *bufA;      // V : CBCA ping-pong
+	float *bufC;      // V : SGM accumulator / ping-pong
 	float *x0c, *x1c; // 4HW each: cross arms (main.lua:993-996)
-	uint32_t *packed; // packed arm lengths of both images (adc_packed_words)
+	uint32_t *packed; // packed arm lengths of both images: bytes (exact kernels) + H/V words (constant-work kernel)
 	int *maxlen;
 	float *maps;      // 8HW: disparity maps and stage outputs
 	float *gauss;     // ks*ks
 	uint8_t *sgmtab;  // SGM penalty-class tables
 	int ks;
+	// tensor maps of the volume buffers (inputs of the TMA-staged CBCA)
+	int ntm;
+	const float *tm_ptr[6];
+	CUtensorMap tm[6];
 	// direction overlap (mccnn_pipeline_set_overlap): the two directions of main.lua:955 are independent
 	// until the LR check, so the second one runs on a side stream with its own ping-pong / SGM buffers,
-	// started when the first reaches its SGM phase: the HBM-bound permutes + SGM scans of one direction
-	// then share the GPU with the issue-bound CBCA iterations of the other.
-	int overlap;      // 0 off, 1 two streams, 2 additionally the permute/SGM phases on high-priority streams
+	// started when the first reaches its SGM phase.
+	int overlap;      // 0 off, 1 two streams, 2 additionally the SGM phases on high-priority streams
 	float *bufA2, *bufC2;
 	uint8_t *sgmtab2;
 	cudaStream_t side_stream, hi_stream[2];
@@ -74,6 +93,29 @@ int dev_alloc(void **p, size_t bytes, size_t *acc)
 	return 0;
 }
 
+// longest arm cross() can produce for this preset, and the CBCA support radius
+int pipe_maxlen(const mccnn_pipeline *p) { return p->prm.L1 > 2 ? p->prm.L1 : 2; }
+
+int add_tensor_map(mccnn_pipeline *p, const float *buf)
+{
+	const int halo = pipe_maxlen(p) - 1;
+	if (halo > adc_cbca_tma_max_halo()) return 0;      // such presets run the exact kernels
+	if (p->ntm >= 6) return ADCENSUS_EINVAL;
+	int bw, bh;
+	adc_cbca_tma_box(halo, &bw, &bh);
+	int rc = adc_tma_encode_volume(&p->tm[p->ntm], buf, p->D, p->H, p->W, p->ld, bw, bh);
+	if (rc) return rc;
+	p->tm_ptr[p->ntm++] = buf;
+	return 0;
+}
+
+const CUtensorMap *find_tensor_map(const mccnn_pipeline *p, const float *buf)
+{
+	for (int i = 0; i < p->ntm; i++)
+		if (p->tm_ptr[i] == buf) return &p->tm[i];
+	return nullptr;
+}
+
 struct DeviceGuard {
 	int prev;
 	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
@@ -93,9 +135,12 @@ extern "C" int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, 
 	if (!p) return ADCENSUS_EINVAL;
 	memset(p, 0, sizeof(*p));
 	p->C = C; p->D = D; p->H = H; p->W = W; p->device = device;
+	p->ld = (W + 3) & ~3;
 	p->prm = *params;
 	p->HW = (long)H * W;
-	p->V = (long)D * p->HW;
+	p->V = (long)D * H * p->ld;
+	const char *ex = getenv("ADCENSUS_CBCA_EXACT");
+	p->cbca_mode = (ex && atoi(ex)) ? 0 : 1;
 	int rc = 0;
 	const size_t f = sizeof(float);
 	if (!rc) rc = dev_alloc((void **)&p->vols, 2 * p->V * f, &p->bytes);
@@ -103,10 +148,15 @@ extern "C" int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, 
 	if (!rc) rc = dev_alloc((void **)&p->bufC, p->V * f, &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->x0c, 4 * p->HW * f, &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->x1c, 4 * p->HW * f, &p->bytes);
-	if (!rc) rc = dev_alloc((void **)&p->packed, adc_packed_words(H, W) * sizeof(uint32_t), &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->packed, (adc_packed_words(H, W) + adc_packed_hv_words(H, W)) * sizeof(uint32_t), &p->bytes);
 	if (!rc) rc = dev_alloc((void **)&p->maxlen, sizeof(int), &p->bytes);
+	if (!rc) rc = (int)cudaMemset(p->maxlen, 0, sizeof(int));
 	if (!rc) rc = dev_alloc((void **)&p->maps, 8 * p->HW * f, &p->bytes);
-	if (!rc) rc = dev_alloc((void **)&p->sgmtab, adc_sgm_table_bytes(H, W, D), &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->sgmtab, adc_sgm_dhw_table_bytes(H, W, D), &p->bytes);
+	if (!rc) rc = add_tensor_map(p, p->vols);
+	if (!rc) rc = add_tensor_map(p, p->vols + p->V);
+	if (!rc) rc = add_tensor_map(p, p->bufA);
+	if (!rc) rc = add_tensor_map(p, p->bufC);
 	p->ks = mccnn_gaussian(params->blur_sigma, nullptr);
 	if (!rc) rc = dev_alloc((void **)&p->gauss, (size_t)p->ks * p->ks * f, &p->bytes);
 	if (!rc) {
@@ -155,14 +205,24 @@ extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
 }
 
 extern "C" size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p) { return p ? p->bytes : 0; }
-// 0 exact (default), 1 per-row prefix sums, 2 experimental constant-work kernel (cbca_o1_kernel); other values -> 1
-extern "C" void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on) { if (p) p->fast_cbca = on == 2 ? 2 : (on ? 1 : 0); }
+// 1 (default) constant-work aggregation within the 1e-4 contract (cbca_tma.cu); 0 exact, bit-identical to the reference
+extern "C" void mccnn_pipeline_set_cbca_mode(mccnn_pipeline *p, int mode) { if (p) p->cbca_mode = mode ? 1 : 0; }
+extern "C" int mccnn_pipeline_get_cbca_mode(const mccnn_pipeline *p) { return p ? p->cbca_mode : -1; }
+extern "C" void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on) { mccnn_pipeline_set_cbca_mode(p, on); }
 static void overlap_release(mccnn_pipeline *p)
 {
 	const size_t f = sizeof(float);
 	if (p->bufA2) { cudaFree(p->bufA2); p->bytes -= p->V * f; }
 	if (p->bufC2) { cudaFree(p->bufC2); p->bytes -= p->V * f; }
-	if (p->sgmtab2) { cudaFree(p->sgmtab2); p->bytes -= adc_sgm_table_bytes(p->H, p->W, p->D); }
+	if (p->sgmtab2) { cudaFree(p->sgmtab2); p->bytes -= adc_sgm_dhw_table_bytes(p->H, p->W, p->D); }
+	for (int i = 0; i < p->ntm;)                       // forget the maps of the released buffers
+		if (p->tm_ptr[i] == p->bufA2 || p->tm_ptr[i] == p->bufC2) {
+			p->tm_ptr[i] = p->tm_ptr[p->ntm - 1];
+			p->tm[i] = p->tm[p->ntm - 1];
+			p->ntm--;
+		} else {
+			i++;
+		}
 	p->bufA2 = p->bufC2 = nullptr;
 	p->sgmtab2 = nullptr;
 	if (p->side_stream) cudaStreamDestroy(p->side_stream);
@@ -187,7 +247,9 @@ extern "C" int mccnn_pipeline_set_overlap(mccnn_pipeline *p, int mode)
 		int rc = 0, lo = 0, hi = 0;
 		if (!rc) rc = dev_alloc((void **)&p->bufA2, p->V * f, &p->bytes);
 		if (!rc) rc = dev_alloc((void **)&p->bufC2, p->V * f, &p->bytes);
-		if (!rc) rc = dev_alloc((void **)&p->sgmtab2, adc_sgm_table_bytes(p->H, p->W, p->D), &p->bytes);
+		if (!rc) rc = dev_alloc((void **)&p->sgmtab2, adc_sgm_dhw_table_bytes(p->H, p->W, p->D), &p->bytes);
+		if (!rc) rc = add_tensor_map(p, p->bufA2);
+		if (!rc) rc = add_tensor_map(p, p->bufC2);
 		if (!rc) rc = (int)cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
 		if (!rc) rc = (int)cudaStreamCreateWithPriority(&p->side_stream, cudaStreamNonBlocking, lo);
 		for (int k = 0; k < 2 && !rc; k++) {
@@ -222,23 +284,44 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 	if (!p || !featL || !featR || !imgL || !imgR || !disp) return ADCENSUS_EINVAL;
 	DeviceGuard g(p->device);
 	cudaStream_t s = adc_stream(stream);
-	const int C = p->C, D = p->D, H = p->H, W = p->W;
+	const int C = p->C, D = p->D, H = p->H, W = p->W, ld = p->ld;
 	const long HW = p->HW, V = p->V;
 	const mccnn_params &o = p->prm;
 	int nl = 0;
 
 	float *volsL = p->vols, *volsR = p->vols + V;
-	STEP(mccnn_fill_invalid(volsL, volsR, D, H, W, s)); nl += 1;                                 // main.lua:946 (only what :947 leaves)
-	STEP(adcensus_StereoJoin(featL, featR, volsL, volsR, C, D, H, W, s)); nl += 1;               // :947
-	STEP(mccnn_fix_border(volsL, D, H, W, o.border, -1, s));                                     // :948
-	STEP(mccnn_fix_border(volsR, D, H, W, o.border, 1, s)); nl += o.border ? 2 : 0;              // :949
+	STEP(adc_fill_invalid(volsL, volsR, D, H, W, ld, s)); nl += 1;                                // main.lua:946 (only what :947 leaves)
+	STEP(adc_stereo_join(featL, featR, volsL, volsR, C, D, H, W, ld, s)); nl += 1;                // :947
+	STEP(adc_fix_border(volsL, D, H, W, ld, o.border, -1, s));                                    // :948
+	STEP(adc_fix_border(volsR, D, H, W, ld, o.border, 1, s)); nl += o.border ? 2 : 0;             // :949
 
 	// cross arms: identical for both directions (main.lua:993-996 recomputes them)
-	const int maxlen = o.L1 > 2 ? o.L1 : 2;  // bound on the arm length cross() can produce
-	STEP(adcensus_cross(imgL, p->x0c, H, W, o.L1, o.tau1, s));
-	STEP(adcensus_cross(imgR, p->x1c, H, W, o.L1, o.tau1, s));
-	STEP(adc_pack_arms(p->x0c, p->packed, 0, H, W, p->maxlen, s));
-	STEP(adc_pack_arms(p->x1c, p->packed, 1, H, W, p->maxlen, s)); nl += 4;
+	const int maxlen = pipe_maxlen(p);       // bound on the arm length cross() can produce
+	const int ncbca = o.cbca_i1 + o.cbca_i2;
+	// fix_border copies column W-n-1 over the border columns: for D > W - n - 1 that column holds NaN at "valid"
+	// positions, which only the tap-by-tap generic kernel treats like the reference (NaN only where a tap is NaN)
+	const bool nan_in_valid = o.border > 0 && D > W - o.border - 1;
+	const bool tma = p->cbca_mode && !nan_in_valid && maxlen - 1 <= adc_cbca_tma_max_halo() && p->ntm > 0;
+	uint32_t *hv = p->packed + adc_packed_words(H, W);
+	if (ncbca > 0) {
+		STEP(adcensus_cross(imgL, p->x0c, H, W, o.L1, o.tau1, s));
+		STEP(adcensus_cross(imgR, p->x1c, H, W, o.L1, o.tau1, s)); nl += 2;
+		if (tma) {
+			STEP(adc_pack_arms_hv(p->x0c, hv, 0, H, W, s));
+			STEP(adc_pack_arms_hv(p->x1c, hv, 1, H, W, s)); nl += 2;
+		} else if (!nan_in_valid) {
+			STEP(adc_pack_arms(p->x0c, p->packed, 0, H, W, p->maxlen, s));
+			STEP(adc_pack_arms(p->x1c, p->packed, 1, H, W, p->maxlen, s)); nl += 2;
+		}
+	}
+	auto cbca = [&](const float *in, float *out, int direction, cudaStream_t ds) -> int {        // adcensus.cbca, :999 / :1036
+		if (tma) {
+			const CUtensorMap *tm = find_tensor_map(p, in);
+			if (!tm) return ADCENSUS_EINVAL;
+			return adc_cbca_tma(tm, hv, in, out, D, H, W, ld, direction, maxlen - 1, ds);
+		}
+		return adc_cbca_packed(p->packed, p->x0c, p->x1c, in, out, D, H, W, ld, direction, nan_in_valid ? (1 << 20) : maxlen, ds);
+	};
 
 	float *dispR = p->maps, *dispL = p->maps + HW;
 	float *final_left = nullptr;
@@ -247,44 +330,46 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 	auto run_direction = [&](int k, cudaStream_t ds, float *cur, float *spare, float *acc, uint8_t *tab) -> int {
 		const int direction = k == 0 ? 1 : -1;                                                   // :955
 		for (int i = 0; i < o.cbca_i1; i++) {                                                    // :998-1001
-			STEP(adc_cbca_packed(p->packed, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, ds, p->fast_cbca));
+			STEP(cbca(cur, spare, direction, ds));
 			float *t = cur; cur = spare; spare = t; nl += 1;
 		}
 		if (k == 0 && p->overlap) STEP((int)cudaEventRecord(p->ev_stagger, ds));                 // the other direction may start
-		cudaStream_t ss = ds;                                                                    // stream of the permute/SGM phase
+		cudaStream_t ss = ds;                                                                    // stream of the SGM phase
 		if (p->overlap == 2 && o.sgm_i > 0) {
 			ss = p->hi_stream[k];
 			STEP((int)cudaEventRecord(p->ev_hi_in[k], ds));
 			STEP((int)cudaStreamWaitEvent(ss, p->ev_hi_in[k], 0));
 		}
-		for (int it = 0; it < o.sgm_i; it++) {                                                   // :1008-1020
-			STEP(mccnn_transpose_dhw_to_hwd(cur, spare, D, H, W, ss));                           // :1008
-			STEP(adc_sgm2(imgL, imgR, spare, acc, tab, H, W, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
-				      o.sgm_q1, o.sgm_q2, direction, /*zero_out=*/true, ss));                    // :1014-1016
-			STEP(mccnn_transpose_hwd_to_dhw_div4(acc, cur, D, H, W, ss));                        // :1017-1020
-			nl += 7;
+		for (int it = 0; it < o.sgm_i; it++) {                                                   // :1008-1020, no permutes: (D,H,ld) scans
+			STEP(adc_sgm2_dhw(imgL, imgR, cur, acc, tab, H, W, ld, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
+					  o.sgm_q1, o.sgm_q2, direction, /*div4=*/true, ss));                  // :1014-1016, :1020
+			float *t = cur; cur = acc; acc = t;
+			nl += 5;
 		}
 		if (ss != ds) {
 			STEP((int)cudaEventRecord(p->ev_hi_out[k], ss));
 			STEP((int)cudaStreamWaitEvent(ds, p->ev_hi_out[k], 0));
 		}
 		for (int i = 0; i < o.cbca_i2; i++) {                                                    // :1035-1038
-			STEP(adc_cbca_packed(p->packed, p->x0c, p->x1c, cur, spare, D, H, W, direction, maxlen, ds, p->fast_cbca));
+			STEP(cbca(cur, spare, direction, ds));
 			float *t = cur; cur = spare; spare = t; nl += 1;
 		}
-		STEP(mccnn_argmin(cur, direction == 1 ? dispR : dispL, D, (int)HW, ds)); nl += 1;        // :1049-1050
+		STEP(adc_argmin_pitched(cur, direction == 1 ? dispR : dispL, D, H, W, ld, ds)); nl += 1; // :1049-1050
 		float *dst = direction == 1 ? volR : volL;                                               // :1042-1047
-		if (dst) STEP((int)cudaMemcpyAsync(dst, cur, V * sizeof(float), cudaMemcpyDeviceToDevice, ds));
+		if (dst) STEP((int)cudaMemcpy2DAsync(dst, (size_t)W * 4, cur, (size_t)ld * 4, (size_t)W * 4, (size_t)D * H,
+						     cudaMemcpyDeviceToDevice, ds));
 		if (direction == -1) final_left = cur;
 		return 0;
 	};
-	if (!p->overlap) {
-		// sequential: the right volume is dead after its argmin, so both of its buffers serve the
-		// left direction as spares (4V of volume buffers in total)
+	// main.lua:954-955: without the LR check (mb) only direction -1 is consumed, unless the caller asks for the
+	// right volume (`-a predict` writes right.bin)
+	const bool need_right = o.lr_check || volR;
+	if (!need_right) {
+		STEP(run_direction(1, s, volsL, p->bufA, p->bufC, p->sgmtab));
+	} else if (!p->overlap) {
+		// sequential: the right direction's three buffers are dead after its argmin / copy-out
 		STEP(run_direction(0, s, volsR, p->bufA, p->bufC, p->sgmtab));
-		// after direction +1, `bufA` or `volsR` is free whichever ended up as its spare: recompute
-		const int flips = o.cbca_i1 + o.cbca_i2;                                                 // ping-pong swaps of direction +1
-		STEP(run_direction(1, s, volsL, (flips & 1) ? volsR : p->bufA, p->bufC, p->sgmtab));
+		STEP(run_direction(1, s, volsL, p->bufA, p->bufC, p->sgmtab));
 	} else {
 		// concurrent: direction -1 on the side stream with its own spare / accumulator / tables,
 		// started when direction +1 leaves its first CBCA block
@@ -304,7 +389,7 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 		STEP(adcensus_interpolate_mismatch(m + 3 * HW, outlier, m + 4 * HW, H, W, s));           // :1063
 		curd = m + 4 * HW; nl += 3;
 	}
-	STEP(adcensus_subpixel_enchancement(curd, final_left, m + 5 * HW, H, W, D, s));              // :1068
+	STEP(adc_subpixel(curd, final_left, m + 5 * HW, H, W, ld, D, s));                            // :1068
 	STEP(adcensus_median2d(m + 5 * HW, m + 6 * HW, H, W, 5, s));                                 // :1073
 	STEP(adcensus_mean2d(m + 6 * HW, p->gauss, disp, H, W, p->ks, o.blur_t, s)); nl += 3;        // :1078
 	p->launches = nl;

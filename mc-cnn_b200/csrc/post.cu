@@ -143,16 +143,19 @@ __global__ void interp_mis_kernel(const float *__restrict__ d0, const float *__r
 	out[id] = vals[n / 2];                                           // :1056
 }
 
-__global__ void subpixel_kernel(const float *__restrict__ d0, const float *__restrict__ c2, float *__restrict__ out, int size, long HW, int disp_max)
+// c2: (disp_max, H, ld) with row pitch ld >= W (ld == W: contiguous)
+__global__ void subpixel_kernel(const float *__restrict__ d0, const float *__restrict__ c2, float *__restrict__ out, int size, int H, int W, int ld, int disp_max)
 {
 	int id = blockIdx.x * blockDim.x + threadIdx.x;
 	if (id >= size) return;
 	int d = (int)d0[id];
 	float res = (float)d;
 	if (1 <= d && d < disp_max - 1) {
-		float cn = c2[(long)(d - 1) * HW + id];
-		float cz = c2[(long)d * HW + id];
-		float cp = c2[(long)(d + 1) * HW + id];
+		const long HW = (long)H * ld;
+		const long pix = (long)(id / W) * ld + id % W;
+		float cn = c2[(long)(d - 1) * HW + pix];
+		float cz = c2[(long)d * HW + pix];
+		float cp = c2[(long)(d + 1) * HW + pix];
 		float denom = 2 * (cp + cn - 2 * cz);                       // :1214
 		if ((double)denom > 1e-5)
 			res = (float)((double)d - fmin(1.0, fmax(-1.0, (double)((cp - cn) / denom)))); // :1216
@@ -357,24 +360,24 @@ __global__ void fill_nan_kernel(float4 *p4, size_t n4, float *tail, int ntail)
 
 // NaN only where StereoJoin writes nothing (main.lua:946 fills everything; the op then overwrites the
 // rest): left volume x < d, right volume x >= W - d.  One thread per (d, y, t), t < d.
-__global__ void fill_invalid_kernel(float *volL, float *volR, int D, int H, int W)
+__global__ void fill_invalid_kernel(float *volL, float *volR, int D, int H, int W, int ld)
 {
 	const int d = blockIdx.y + 1;                  // d = 0 has no invalid entries
 	const int n = min(d, W);
-	const long HW = (long)H * W;
+	const long HW = (long)H * ld;
 	const float q = adc_nan();
 	for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)H * n; i += (long)gridDim.x * blockDim.x) {
 		const int y = (int)(i / n), t = (int)(i % n);
-		volL[d * HW + (long)y * W + t] = q;
-		volR[d * HW + (long)y * W + (W - 1 - t)] = q;
+		volL[d * HW + (long)y * ld + t] = q;
+		volR[d * HW + (long)y * ld + (W - 1 - t)] = q;
 	}
 }
 
-__global__ void fix_border_kernel(float *vol, long rows, int W, int n, int direction)
+__global__ void fix_border_kernel(float *vol, long rows, int W, int ld, int n, int direction)
 {
 	long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= rows) return;
-	float *row = vol + r * W;
+	float *row = vol + r * ld;
 	float v = row[direction > 0 ? n : W - n - 1];
 	for (int i = 1; i <= n; i++) row[direction > 0 ? i - 1 : W - i] = v;
 }
@@ -459,6 +462,68 @@ int adc_transpose(const float *in, float *out, long R, long Cn, float div, bool 
 	return 0;
 }
 
+// first minimum over D of a pitched (D, H, ld) volume, 0-based, NaN skipped (main.lua:1049-1050; strict <, init +inf
+// like spatial_argmin, adcensus.cu:251-259)
+__global__ void argmin_pitched_kernel(const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int ld)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+	if (x >= W) return;
+	const long HW = (long)H * ld;
+	const float *v = vol + (long)y * ld + x;
+	int arg = 0;
+	float mn = CUDART_INF_F;
+	int d = 0;
+	for (; d + 4 <= D; d += 4) {
+		float a = ld_stream(v + (long)d * HW), b = ld_stream(v + (long)(d + 1) * HW);
+		float c = ld_stream(v + (long)(d + 2) * HW), e = ld_stream(v + (long)(d + 3) * HW);
+		if (a < mn) { mn = a; arg = d; }
+		if (b < mn) { mn = b; arg = d + 1; }
+		if (c < mn) { mn = c; arg = d + 2; }
+		if (e < mn) { mn = e; arg = d + 3; }
+	}
+	for (; d < D; d++) {
+		float a = ld_stream(v + (long)d * HW);
+		if (a < mn) { mn = a; arg = d; }
+	}
+	out[(long)y * W + x] = (float)arg;
+}
+
+// ---- pitched (D, H, ld) forms used by the fused pipeline (ld == W: the API-facing contiguous tensors) ----
+int adc_argmin_pitched(const float *vol, float *disp, int D, int H, int W, int ld, cudaStream_t s)
+{
+	if (!vol || !disp || D < 1 || H < 1 || W < 1 || ld < W || H > 65535) return ADCENSUS_EINVAL;
+	dim3 grid(adc_div_up(W, 128), H);
+	argmin_pitched_kernel<<<grid, 128, 0, s>>>(vol, disp, D, H, W, ld);
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+int adc_subpixel(const float *d0, const float *c2, float *out, int H, int W, int ld, int disp_max, cudaStream_t s)
+{
+	if (!d0 || !c2 || !out || H < 1 || W < 1 || ld < W || disp_max < 1) return ADCENSUS_EINVAL;
+	LAUNCH1D(subpixel_kernel, H * W, s, d0, c2, out, H * W, H, W, ld, disp_max);
+	return 0;
+}
+
+int adc_fill_invalid(float *volL, float *volR, int D, int H, int W, int ld, cudaStream_t s)
+{
+	if (!volL || !volR || D < 1 || H < 1 || W < 1 || ld < W) return ADCENSUS_EINVAL;
+	if (D == 1) return 0;
+	dim3 grid(8, D - 1);
+	fill_invalid_kernel<<<grid, 256, 0, s>>>(volL, volR, D, H, W, ld);
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+int adc_fix_border(float *vol, int D, int H, int W, int ld, int n, int direction, cudaStream_t s)
+{
+	if (!vol || D < 1 || H < 1 || W < 1 || ld < W || n < 0 || n + 1 > W || (direction != 1 && direction != -1)) return ADCENSUS_EINVAL;
+	if (n == 0) return 0;
+	long rows = (long)D * H;
+	LAUNCH1D(fix_border_kernel, rows, s, vol, rows, W, ld, n, direction);
+	return 0;
+}
+
 extern "C" {
 
 int adcensus_spatial_argmin(const float *input, float *output, int N, int D, int HW, adcensus_stream_t stream)
@@ -505,9 +570,7 @@ int adcensus_interpolate_mismatch(const float *d0, const float *outlier, float *
 
 int adcensus_subpixel_enchancement(const float *d0, const float *c2, float *out, int H, int W, int disp_max, adcensus_stream_t stream)
 {
-	if (!d0 || !c2 || !out || H < 1 || W < 1 || disp_max < 1) return ADCENSUS_EINVAL;
-	LAUNCH1D(subpixel_kernel, H * W, adc_stream(stream), d0, c2, out, H * W, (long)H * W, disp_max);
-	return 0;
+	return adc_subpixel(d0, c2, out, H, W, W, disp_max, adc_stream(stream));
 }
 
 int adcensus_median2d(const float *img, float *out, int H, int W, int kernel_size, adcensus_stream_t stream)
@@ -588,21 +651,12 @@ int mccnn_fill_nan(float *p, size_t n, adcensus_stream_t stream)
 
 int mccnn_fill_invalid(float *volL, float *volR, int D, int H, int W, adcensus_stream_t stream)
 {
-	if (!volL || !volR || D < 1 || H < 1 || W < 1) return ADCENSUS_EINVAL;
-	if (D == 1) return 0;
-	dim3 grid(8, D - 1);
-	fill_invalid_kernel<<<grid, 256, 0, adc_stream(stream)>>>(volL, volR, D, H, W);
-	ADC_CHECK_LAUNCH();
-	return 0;
+	return adc_fill_invalid(volL, volR, D, H, W, W, adc_stream(stream));
 }
 
 int mccnn_fix_border(float *vol, int D, int H, int W, int n, int direction, adcensus_stream_t stream)
 {
-	if (!vol || D < 1 || H < 1 || W < 1 || n < 0 || n + 1 > W || (direction != 1 && direction != -1)) return ADCENSUS_EINVAL;
-	if (n == 0) return 0;
-	long rows = (long)D * H;
-	LAUNCH1D(fix_border_kernel, rows, adc_stream(stream), vol, rows, W, n, direction);
-	return 0;
+	return adc_fix_border(vol, D, H, W, W, n, direction, adc_stream(stream));
 }
 
 int mccnn_transpose_dhw_to_hwd(const float *in, float *out, int D, int H, int W, adcensus_stream_t stream)

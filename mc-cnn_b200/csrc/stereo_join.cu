@@ -67,7 +67,7 @@ template <int NS>
 __global__ void __launch_bounds__(16 * NS, (NS >= 6) ? 3 : 4)
 stereo_join_kernel(const float *__restrict__ gL, const float *__restrict__ gR,
 		   float *__restrict__ outL, float *__restrict__ outR,
-		   int C, int D, int H, int W)
+		   int C, int D, int H, int W, int ldo)
 {
 	using Cfg = SJCfg<NS>;
 	constexpr int DC = Cfg::DC, NT = Cfg::NT;
@@ -206,7 +206,7 @@ stereo_join_kernel(const float *__restrict__ gL, const float *__restrict__ gR,
 		const int x = X0 + xl;
 		if (x < W && x >= d) {
 			const float v = so[r * SJ_TX + split_pos(xl, 16)];
-			const long rowbase = (long)d * HW + (long)y * W;
+			const long rowbase = ((long)d * H + y) * ldo;   // outputs are (D, H, ldo), ldo >= W
 			outL[rowbase + x] = v;       // adcensus.cu:1472
 			outR[rowbase + x - d] = v;   // adcensus.cu:1473
 		}
@@ -214,7 +214,7 @@ stereo_join_kernel(const float *__restrict__ gL, const float *__restrict__ gR,
 }
 
 template <int NS>
-int launch(const float *L, const float *R, float *outL, float *outR, int C, int D, int H, int W, cudaStream_t s)
+int launch(const float *L, const float *R, float *outL, float *outR, int C, int D, int H, int W, int ldo, cudaStream_t s)
 {
 	using Cfg = SJCfg<NS>;
 	static bool attr_done[64] = {false};
@@ -225,32 +225,38 @@ int launch(const float *L, const float *R, float *outL, float *outR, int C, int 
 		attr_done[dev & 63] = true;
 	}
 	dim3 grid(adc_div_up(W, SJ_TX), H, adc_div_up(D, Cfg::DC));
-	stereo_join_kernel<NS><<<grid, Cfg::NT, Cfg::SMEM, s>>>(L, R, outL, outR, C, D, H, W);
+	stereo_join_kernel<NS><<<grid, Cfg::NT, Cfg::SMEM, s>>>(L, R, outL, outR, C, D, H, W, ldo);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
 
 }  // namespace
 
-extern "C" int adcensus_StereoJoin(const float *input_L, const float *input_R, float *output_L, float *output_R,
-				   int C, int D, int H, int W, adcensus_stream_t stream)
+// outputs (D, H, ldo) with row pitch ldo >= W (the fused pipeline's private volumes); features (C, H, W) contiguous
+int adc_stereo_join(const float *input_L, const float *input_R, float *output_L, float *output_R,
+		    int C, int D, int H, int W, int ldo, cudaStream_t s)
 {
 	if (!input_L || !input_R || !output_L || !output_R) return ADCENSUS_EINVAL;
-	if (C < 1 || D < 1 || H < 1 || W < 1 || H > 65535) return ADCENSUS_EINVAL;
+	if (C < 1 || D < 1 || H < 1 || W < 1 || H > 65535 || ldo < W) return ADCENSUS_EINVAL;
 	if (C > 128) return ADCENSUS_ELIMIT;  // reference: float L_cache[128] (adcensus.cu:1460-1461)
-	cudaStream_t s = adc_stream(stream);
 	// split D into equal chunks of at most 120 and pick the smallest tile count that covers one
 	const int nchunk = adc_div_up(D, 120);
 	const int dc = adc_div_up(D, nchunk);
 	const int ns = adc_div_up(dc + 8, 16);
 	switch (ns) {
-	case 1: return launch<1>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	case 2: return launch<2>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	case 3: return launch<3>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	case 4: return launch<4>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	case 5: return launch<5>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	case 6: return launch<6>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	case 7: return launch<7>(input_L, input_R, output_L, output_R, C, D, H, W, s);
-	default: return launch<8>(input_L, input_R, output_L, output_R, C, D, H, W, s);
+	case 1: return launch<1>(input_L, input_R, output_L, output_R, C, D, H, W, ldo, s);
+	case 2: return launch<2>(input_L, input_R, output_L, output_R, C, D, H, W, ldo, s);
+	case 3: return launch<3>(input_L, input_R, output_L, output_R, C, D, H, W, ldo, s);
+	case 4: return launch<4>(input_L, input_R, output_L, output_R, C, D, H, W, ldo, s);
+	case 5: return launch<5>(input_L, input_R, output_L, output_R, C, D, H, W, ldo, s);
+	case 6: return launch<6>(input_L, input_R, output_L, output_R, C, D, H, W, ldo, s);
+	case 7: return launch<7>(input_L, input_R, output_L, output_R, C, D, H, W, ldo, s);
+	default: return launch<8>(input_L, input_R, output_L, output_R, C, D, H, W, ldo, s);
 	}
+}
+
+extern "C" int adcensus_StereoJoin(const float *input_L, const float *input_R, float *output_L, float *output_R,
+				   int C, int D, int H, int W, adcensus_stream_t stream)
+{
+	return adc_stereo_join(input_L, input_R, output_L, output_R, C, D, H, W, W, adc_stream(stream));
 }

@@ -155,13 +155,17 @@ def stereo_predict(x_batch, features, opt, disp_max, want_vols=False, arch="fast
 class StereoPipeline:
     """Native fused stereo_predict (mccnn_pipeline_*): buffers allocated once per (C,D,H,W)."""
 
-    def __init__(self, C, D, H, W, params, device=0):
+    def __init__(self, C, D, H, W, params, device=0, cbca_mode=None):
+        """``cbca_mode``: "fast" (library default) = constant-work aggregation inside the north star's 1e-4 contract
+        for float aggregation; "exact" = tap-by-tap sums, volumes bit-identical to the reference."""
         self.C, self.D, self.H, self.W = C, D, H, W
         self.params = params
         self.device = int(device)
         self._h = ctypes.c_void_p()
         rc = adcensus.lib().mccnn_pipeline_create(ctypes.byref(self._h), C, D, H, W, ctypes.byref(params), self.device)
         adcensus._check(rc, "mccnn_pipeline_create")
+        if cbca_mode is not None:
+            self.set_cbca_mode(cbca_mode)
 
     def close(self):
         if self._h:
@@ -178,11 +182,19 @@ class StereoPipeline:
         """Run the two directions concurrently on two streams (mccnn_pipeline_set_overlap); results are unchanged."""
         adcensus._check(adcensus.lib().mccnn_pipeline_set_overlap(self._h, int(mode)), "mccnn_pipeline_set_overlap")
 
+    def set_cbca_mode(self, mode):
+        """"fast" / 1: constant-work CBCA (csrc/cbca_tma.cu, ~1e-6 relative to the tap-by-tap sums, bar 1e-4);
+        "exact" / 0: bit-identical to the reference (mccnn_pipeline_set_cbca_mode)."""
+        m = {"fast": 1, "exact": 0}.get(mode, mode)
+        adcensus.lib().mccnn_pipeline_set_cbca_mode(self._h, int(bool(m)))
+
+    @property
+    def cbca_mode(self):
+        return "fast" if adcensus.lib().mccnn_pipeline_get_cbca_mode(self._h) else "exact"
+
     def set_fast_cbca(self, on=True):
-        """Opt in to the approximate CBCA kernel (prefix sums per support row: ~1e-6 relative to the
-        exact-order kernel, not bit-exact with the reference).  Default is exact."""
-        level = int(on) if isinstance(on, int) and not isinstance(on, bool) else int(bool(on))   # 2 = experimental kernel
-        adcensus.lib().mccnn_pipeline_set_fast_cbca(self._h, level)
+        """older name of :meth:`set_cbca_mode`"""
+        self.set_cbca_mode(1 if on else 0)
 
     @property
     def device_bytes(self):

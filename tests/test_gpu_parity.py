@@ -269,7 +269,7 @@ def test_pipeline_vs_oracle(oracle, H, W, C, D, preset, over):
     same(vR, wR, "right.bin (op chain)")
     same(d, want, "disp.bin (op chain)")
     # (b) the fused native pipeline
-    sp = pipeline.StereoPipeline(C, D, H, W, opt)
+    sp = pipeline.StereoPipeline(C, D, H, W, opt, cbca_mode="exact")
     volL = torch.empty((D, H, W), device=dev())
     volR = torch.empty((D, H, W), device=dev())
     disp = sp.run(feats[0], feats[1], x_batch[0, 0], x_batch[1, 0], volL=volL, volR=volR)
@@ -352,7 +352,7 @@ def test_against_golden(golden_dir):
                                  for k, v in zip(g["opt_names"], g["opt_values"])})
         x_batch = cu(np.stack([g["imgL"], g["imgR"]])[:, None])
         feats = cu(np.stack([g["featL"], g["featR"]]))
-        sp = pipeline.StereoPipeline(C, D, H, W, opt)
+        sp = pipeline.StereoPipeline(C, D, H, W, opt, cbca_mode="exact")
         volL = torch.empty((D, H, W), device=dev())
         disp = sp.run(feats[0], feats[1], x_batch[0, 0], x_batch[1, 0], volL=volL)
         same(disp, g["disp"][0, 0], os.path.basename(f) + " disp")
@@ -377,7 +377,7 @@ def test_against_live_reference():
         x_batch = cu(np.stack([p["imgL"], p["imgR"]])[:, None])
         feats = cu(np.stack([p["featL"], p["featR"]]))
         want, wL, wR = refdriver.stereo_predict(shim, x_batch, feats, opt, D, want_vols=True)
-        sp = pipeline.StereoPipeline(C, D, H, W, opt)
+        sp = pipeline.StereoPipeline(C, D, H, W, opt, cbca_mode="exact")
         volL = torch.empty((D, H, W), device=dev())
         volR = torch.empty((D, H, W), device=dev())
         disp = sp.run(feats[0], feats[1], x_batch[0, 0], x_batch[1, 0], volL=volL, volR=volR)
@@ -408,7 +408,7 @@ def test_full_size_against_live_reference(H, W, C, D, preset, over):
     x_batch = cu(np.stack([p["imgL"], p["imgR"]])[:, None])
     feats = cu(np.stack([p["featL"], p["featR"]]))
     want, wL, wR = refdriver.stereo_predict(shim, x_batch, feats, opt, D, want_vols=True)
-    sp = pipeline.StereoPipeline(C, D, H, W, opt)
+    sp = pipeline.StereoPipeline(C, D, H, W, opt, cbca_mode="exact")
     volL = torch.empty((D, H, W), device=dev())
     volR = torch.empty((D, H, W), device=dev())
     disp = sp.run(feats[0], feats[1], x_batch[0, 0], x_batch[1, 0], volL=volL, volR=volR)
@@ -427,10 +427,11 @@ def test_full_size_against_live_reference(H, W, C, D, preset, over):
     sp.close()
 
 
-def test_fast_cbca_mode_is_within_tolerance(oracle):
-    """The opt-in prefix-sum CBCA is NOT bit-exact: volumes must agree with the oracle within the north
-    star's 1e-4 (they do to ~1e-6), NaN positions exactly, and the final disparity map may differ only
-    at isolated near-tie pixels."""
+def test_default_cbca_mode_is_within_tolerance(oracle):
+    """The pipeline's DEFAULT CBCA (constant-work, csrc/cbca_tma.cu) is not bit-exact: volumes must agree with the
+    oracle within the north star's 1e-4 (they do to ~1e-6), NaN positions exactly, and the final disparity map may
+    differ only at isolated near-tie pixels (<= 1e-4 on >= (1 - 1e-4) of the pixels is the bar at the
+    bench sizes; this small, noisy synthetic pair gets a looser count)."""
     H, W, C, D = 96, 200, 16, 40
     opt = pipeline.make_params("kitti", "accurate_cbca4")
     p = synth.make_pair(H, W, C, D, seed=4)
@@ -438,7 +439,7 @@ def test_fast_cbca_mode_is_within_tolerance(oracle):
                                          oracle.Params(**opt.as_dict()), want_vols=True)
     t = lambda a: cu(a)
     sp = pipeline.StereoPipeline(C, D, H, W, opt)
-    sp.set_fast_cbca(True)
+    assert sp.cbca_mode == "fast"
     volL = torch.empty((D, H, W), device=dev())
     volR = torch.empty((D, H, W), device=dev())
     disp = sp.run(t(p["featL"]), t(p["featR"]), t(p["imgL"]), t(p["imgR"]), volL=volL, volR=volR)
@@ -450,40 +451,13 @@ def test_fast_cbca_mode_is_within_tolerance(oracle):
         assert err.max() <= 1e-4, "%s: max relative error %.3g above 1e-4" % (what, err.max())
     d = disp.cpu().numpy()
     frac = float((np.abs(d - want) > 1e-4 * np.maximum(1.0, np.abs(want))).mean())
-    assert frac < 5e-3, "fast CBCA changed %.4f of the disparity map" % frac
-    # the default (exact) mode stays bit-identical
-    sp.set_fast_cbca(False)
-    same(sp.run(t(p["featL"]), t(p["featR"]), t(p["imgL"]), t(p["imgR"])), want, "exact mode after toggling")
+    assert frac < 5e-3, "constant-work CBCA changed %.4f of the disparity map" % frac
+    # the exact mode stays bit-identical and selectable
+    sp.set_cbca_mode("exact")
+    vL = torch.empty((D, H, W), device=dev())
+    same(sp.run(t(p["featL"]), t(p["featR"]), t(p["imgL"]), t(p["imgR"]), volL=vL), want, "exact mode after toggling")
+    same(vL, wL, "left.bin, exact mode")
     sp.close()
-
-
-@pytest.mark.skipif(os.environ.get("MCCNN_EXPERIMENTAL") != "1",
-                    reason="experimental kernel (cbca level 2), not yet validated on hardware: set MCCNN_EXPERIMENTAL=1")
-@pytest.mark.parametrize("L1,tau1,direction", [(5, 0.13, -1), (5, 0.13, 1), (14, 0.02, -1), (2, 0.5, 1), (9, 5.0, -1)])
-def test_experimental_constant_work_cbca(oracle, L1, tau1, direction):
-    """cbca level 2 (prefix sums along x and y, oracle/cbca_prefix_model.py): within the 1e-4 bar, NaN pattern exact"""
-    import ctypes
-
-    H, W, C, D = 70, 300, 8, 36
-    p = synth.make_pair(H, W, C, D, seed=L1)
-    volL, volR = oracle.stereo_join(p["featL"], p["featR"], D)
-    vol = volL if direction == -1 else volR
-    x0c, x1c = oracle.cross(p["imgL"], L1, tau1), oracle.cross(p["imgR"], L1, tau1)
-    want = oracle.cbca(x0c, x1c, vol, direction)
-    lib = adcensus.lib()
-    lib.mccnn_packed_arms_bytes.restype = ctypes.c_size_t
-    a0, a1, v = cu(x0c)[None], cu(x1c)[None], cu(vol)[None]
-    packed = torch.empty(lib.mccnn_packed_arms_bytes(H, W), dtype=torch.uint8, device=dev())
-    out = torch.empty_like(v)
-    vp = lambda t_: ctypes.c_void_p(t_.data_ptr())
-    assert lib.mccnn_pack_arms(vp(a0), vp(a1), vp(packed), H, W, adcensus._stream(a0)) == 0
-    assert lib.mccnn_cbca_packed_level(vp(packed), vp(a0), vp(a1), vp(v), vp(out), D, H, W, direction, max(L1, 2), 2,
-                                       adcensus._stream(v)) == 0
-    g = out[0].cpu().numpy()
-    assert np.array_equal(np.isnan(g), np.isnan(want))
-    m = ~np.isnan(want)
-    err = np.abs(g[m] - want[m]) / np.maximum(1.0, np.abs(want[m]))
-    assert err.max() <= 1e-4, "max relative error %.3g" % err.max()
 
 
 def test_lua_face_through_the_reference_driver(oracle):

@@ -14,23 +14,24 @@ from mccnn_b200 import pipeline  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=10)
-ap.add_argument("--fast", action="store_true")
-ap.add_argument("--fast-level", type=int, default=0, help="CBCA level: 1 = per-row prefix sums, 2 = experimental constant-work kernel")
+ap.add_argument("--exact", action="store_true", help="exact (bit-identical) CBCA instead of the default constant-work kernel")
+ap.add_argument("--overlap", type=int, default=-1)
+ap.add_argument("--preset", default="accurate_cbca4")
 ap.add_argument("--D", type=int, default=228)
 ap.add_argument("--H", type=int, default=370)
 ap.add_argument("--W", type=int, default=1226)
 ap.add_argument("--C", type=int, default=64)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-opt = pipeline.make_params("kitti", "accurate_cbca4")
+opt = pipeline.make_params("kitti", a.preset)
 g = torch.Generator(device=dev).manual_seed(0)
 fL = torch.nn.functional.normalize(torch.randn((a.C, a.H, a.W), device=dev, generator=g), dim=0)
 fR = torch.nn.functional.normalize(torch.randn((a.C, a.H, a.W), device=dev, generator=g), dim=0)
 iL = torch.randn((a.H, a.W), device=dev, generator=g)
 iR = torch.randn((a.H, a.W), device=dev, generator=g)
-sp = pipeline.StereoPipeline(a.C, a.D, a.H, a.W, opt)
-if a.fast or a.fast_level:
-    sp.set_fast_cbca(a.fast_level if a.fast_level else True)
+sp = pipeline.StereoPipeline(a.C, a.D, a.H, a.W, opt, cbca_mode="exact" if a.exact else "fast")
+if a.overlap >= 0:
+    sp.set_overlap(a.overlap)
 for _ in range(3):
     sp.run(fL, fR, iL, iR)
 torch.cuda.synchronize()
@@ -40,6 +41,6 @@ for _ in range(a.iters):
     sp.run(fL, fR, iL, iR)
 e1.record()
 torch.cuda.synchronize()
-print("dch=%s cbca_level=%d ms_per_pair=%.4f" % (os.environ.get("ADCENSUS_CBCA_DCH", "default"),
-                                                  a.fast_level if a.fast_level else int(a.fast), e0.elapsed_time(e1) / a.iters))
+print("preset=%s dch=%s cbca=%s overlap=%s ms_per_pair=%.4f launches=%d" % (a.preset, os.environ.get("ADCENSUS_CBCA_DCH", "default"), sp.cbca_mode,
+                                                                    a.overlap, e0.elapsed_time(e1) / a.iters, sp.launches_per_run))
 sp.close()
