@@ -203,6 +203,10 @@ size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p);
 void mccnn_pipeline_set_cbca_mode(mccnn_pipeline *p, int mode);
 int mccnn_pipeline_get_cbca_mode(const mccnn_pipeline *p);
 void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on);
+/* SGM data layout inside the pipeline: 0 (default) = permute the pitched volume to (H,W,D) and back around sgm2 like
+ * main.lua:1008-1020 (fused /4); 1 = scan the (D,H,ld) layout directly (mccnn_sgm2_dhw, no permutes).  Bit-identical
+ * results either way; ADCENSUS_SGM_DHW=1 in the environment makes 1 the default. */
+void mccnn_pipeline_set_sgm_layout(mccnn_pipeline *p, int dhw);
 /* opt-in: run the two directions of main.lua:955 concurrently (0 = off: one stream, 4V of volume buffers;
  * 1 = direction -1 on a side stream with its own 2V + tables, started when direction +1 reaches its SGM phase;
  * 2 = additionally the permute / SGM phases on high-priority streams).  Results are identical in every mode

@@ -12,7 +12,8 @@
 // The bit-exact kernels stay in cross_cbca.cu and remain selectable.
 //
 // Per CTA: a 32 x 128 pixel tile, a chunk of `dch` disparities.
-//   * the plane tile (+halo, zero-filled outside the image) of every disparity arrives by ONE TMA box
+//   * the plane tile (+halo, zero-filled outside the image; its first column 16-byte aligned, which the TMA
+//     requires of the innermost coordinate) of every disparity arrives by ONE TMA box
 //     (cp.async.bulk.tensor.3d on the (W, H, D) view of the pitched volume), double-buffered on two
 //     mbarriers: plane d + 2 streams in while d + 1 is processed;
 //   * row prefix sums in place: thread = (row, segment of SEG floats), float4 accesses at a stride that is
@@ -37,8 +38,9 @@ constexpr int CT_WW = CT_TX + CT_DCH;      // pitch of the right-image arm windo
 template <int R>
 struct CTCfg {
 	static constexpr int HALO = R + 1;                 // the prefix differences index the first EXCLUDED pixel
+	static constexpr int HX = (HALO + 3) & ~3;         // left halo in columns: TMA needs a 16-byte aligned start along x
 	static constexpr int TH = CT_TY + 2 * R + 1;       // image rows y0 - HALO .. y0 + TY + R - 1
-	static constexpr int TWMIN = CT_TX + 2 * R + 1;    // image columns x0 - HALO .. x0 + TX + R - 1
+	static constexpr int TWMIN = HX + CT_TX + R;       // image columns x0 - HX .. x0 + TX + R - 1
 	static constexpr int SEG = R <= 4 ? 28 : 20;       // floats per prefix segment: SEG / 4 odd => conflict-free float4
 	static constexpr int NSEG = (TWMIN + SEG - 1) / SEG;
 	static constexpr int TWP = NSEG * SEG;             // tile pitch = TMA box width (140 / 160 floats)
@@ -65,7 +67,7 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		int D, int H, int W, int ld, int direction, int dch)
 {
 	using C = CTCfg<R>;
-	constexpr int HALO = C::HALO, TH = C::TH, TWP = C::TWP, SEG = C::SEG, NSEG = C::NSEG, RING = C::RING, NWALK = C::NWALK;
+	constexpr int HALO = C::HALO, HX = C::HX, TH = C::TH, TWP = C::TWP, SEG = C::SEG, NSEG = C::NSEG, RING = C::RING, NWALK = C::NWALK;
 	extern __shared__ __align__(128) unsigned char ct_smem[];
 	float2 *ring = reinterpret_cast<float2 *>(ct_smem + C::OFF_RING);       // [RING][CT_NT] (T, N) per thread
 	uint32_t *winH = reinterpret_cast<uint32_t *>(ct_smem + C::OFF_WINH);   // [TH][CT_WW] right-image H words
@@ -98,7 +100,7 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		for (int s = 0; s < 2; s++)
 			if (s < nproc) {
 				mbar_arrive_expect_tx(&bars[s], C::TILE_BYTES);
-				tma_load_3d(ct_smem + s * C::STAGE_BYTES, &tmap, x0 - HALO, y0 - HALO, d0 + s, &bars[s]);
+				tma_load_3d(ct_smem + s * C::STAGE_BYTES, &tmap, x0 - HX, y0 - HALO, d0 + s, &bars[s]);
 			}
 	}
 
@@ -137,7 +139,7 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		const int off = (x0 + sh) - a1x0;                 // window column of tile column 0
 		// does the tile hold entries of the invalid triangle (NaN)?  They never lie inside a run, but a
 		// prefix sum would carry them along the row: count them as 0.
-		const bool clean = direction < 0 ? (x0 - HALO - d < 0) : (x0 + CT_TX + R + d >= W);
+		const bool clean = direction < 0 ? (x0 - HX - d < 0) : (x0 + CT_TX + R + d >= W);
 		mbar_wait(&bars[s], (dd >> 1) & 1);
 
 		// 1. inclusive prefix of every tile row, in place
@@ -185,7 +187,7 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		// H words hold 4L | 4(R-1) << 16 (byte offsets into the prefix row), V words U << 8 | (D << 8) << 16
 		// (x 8 = byte offsets into the ring, whose rows are CT_NT * 8 = 2048 bytes apart); the ring carries
 		// (4T, 4N): the factor drops out of the quotient.
-		const char *Pc = reinterpret_cast<const char *>(P + (CT_HO * h) * TWP + c + HALO);   // own pixel's prefix entry, relative row 0
+		const char *Pc = reinterpret_cast<const char *>(P + (CT_HO * h) * TWP + c + HX);   // own pixel's prefix entry, relative row 0
 		const uint32_t *wh = winH + (CT_HO * h) * CT_WW + c + off;
 		const uint16_t *wv = winV + (CT_HO * h) * CT_WW + c + off;
 		char *rgb = reinterpret_cast<char *>(ring + tid);
@@ -235,7 +237,7 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		if (tid == 0 && dd + 2 < nproc) {
 			fence_proxy_async_smem();                      // generic-proxy writes (the in-place prefix) before the TMA refill
 			mbar_arrive_expect_tx(&bars[s], C::TILE_BYTES);
-			tma_load_3d(P, &tmap, x0 - HALO, y0 - HALO, d + 2, &bars[s]);
+			tma_load_3d(P, &tmap, x0 - HX, y0 - HALO, d + 2, &bars[s]);
 		}
 	}
 	for (int dd = nproc; dd < dn; dd++) {                  // tiles entirely inside the invalid triangle: plain copy

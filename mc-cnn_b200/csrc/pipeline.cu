@@ -30,6 +30,12 @@ int adc_cbca_tma_max_halo();
 void adc_cbca_tma_box(int halo, int *box_w, int *box_h);
 int adc_cbca_tma(const CUtensorMap *tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
 		 int halo, cudaStream_t s);
+size_t adc_sgm_table_bytes(int H, int W, int D);
+int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, uint8_t *tab, int H, int W, int D,
+	     float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
+	     bool zero_out, cudaStream_t s);
+int adc_transpose_dhw_pitched_to_hwd(const float *in, float *out, int D, int H, int W, int ld, cudaStream_t s);
+int adc_transpose_hwd_to_dhw_pitched_div4(const float *in, float *out, int D, int H, int W, int ld, cudaStream_t s);
 size_t adc_sgm_dhw_table_bytes(int H, int W, int D);
 int adc_sgm2_dhw(const float *x0, const float *x1, const float *in, float *acc, uint8_t *tab, int H, int W, int ld, int D,
 		 float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction, bool div4, cudaStream_t s);
@@ -51,6 +57,8 @@ struct mccnn_pipeline {
 	size_t bytes;
 	int launches;
 	int cbca_mode;    // 1 = constant-work aggregation (default, 1e-4 contract), 0 = exact (bit-identical to the reference)
+	int sgm_dhw;      // 1 = scan the (D,H,ld) layout directly (sgm_dhw.cu, no permutes); 0 (default) = permute to (H,W,D) like main.lua:1008
+	size_t tab_bytes;
 	// device buffers
 	float *vols;      // 2V: [0] left volume, [1] right volume (main.lua:946)
 	float *bufA;      // V : CBCA ping-pong
@@ -141,6 +149,10 @@ extern "C" int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, 
 	p->V = (long)D * H * p->ld;
 	const char *ex = getenv("ADCENSUS_CBCA_EXACT");
 	p->cbca_mode = (ex && atoi(ex)) ? 0 : 1;
+	const char *sd = getenv("ADCENSUS_SGM_DHW");
+	p->sgm_dhw = (sd && atoi(sd)) ? 1 : 0;
+	p->tab_bytes = adc_sgm_table_bytes(H, W, D);
+	if (adc_sgm_dhw_table_bytes(H, W, D) > p->tab_bytes) p->tab_bytes = adc_sgm_dhw_table_bytes(H, W, D);
 	int rc = 0;
 	const size_t f = sizeof(float);
 	if (!rc) rc = dev_alloc((void **)&p->vols, 2 * p->V * f, &p->bytes);
@@ -152,7 +164,7 @@ extern "C" int mccnn_pipeline_create(mccnn_pipeline **out, int C, int D, int H, 
 	if (!rc) rc = dev_alloc((void **)&p->maxlen, sizeof(int), &p->bytes);
 	if (!rc) rc = (int)cudaMemset(p->maxlen, 0, sizeof(int));
 	if (!rc) rc = dev_alloc((void **)&p->maps, 8 * p->HW * f, &p->bytes);
-	if (!rc) rc = dev_alloc((void **)&p->sgmtab, adc_sgm_dhw_table_bytes(H, W, D), &p->bytes);
+	if (!rc) rc = dev_alloc((void **)&p->sgmtab, p->tab_bytes, &p->bytes);
 	if (!rc) rc = add_tensor_map(p, p->vols);
 	if (!rc) rc = add_tensor_map(p, p->vols + p->V);
 	if (!rc) rc = add_tensor_map(p, p->bufA);
@@ -209,12 +221,14 @@ extern "C" size_t mccnn_pipeline_device_bytes(const mccnn_pipeline *p) { return 
 extern "C" void mccnn_pipeline_set_cbca_mode(mccnn_pipeline *p, int mode) { if (p) p->cbca_mode = mode ? 1 : 0; }
 extern "C" int mccnn_pipeline_get_cbca_mode(const mccnn_pipeline *p) { return p ? p->cbca_mode : -1; }
 extern "C" void mccnn_pipeline_set_fast_cbca(mccnn_pipeline *p, int on) { mccnn_pipeline_set_cbca_mode(p, on); }
+// 0 (default): permute to (H,W,D) for sgm2 like main.lua:1008; 1: scan (D,H,ld) directly (sgm_dhw.cu).  Same results.
+extern "C" void mccnn_pipeline_set_sgm_layout(mccnn_pipeline *p, int dhw) { if (p) p->sgm_dhw = dhw ? 1 : 0; }
 static void overlap_release(mccnn_pipeline *p)
 {
 	const size_t f = sizeof(float);
 	if (p->bufA2) { cudaFree(p->bufA2); p->bytes -= p->V * f; }
 	if (p->bufC2) { cudaFree(p->bufC2); p->bytes -= p->V * f; }
-	if (p->sgmtab2) { cudaFree(p->sgmtab2); p->bytes -= adc_sgm_dhw_table_bytes(p->H, p->W, p->D); }
+	if (p->sgmtab2) { cudaFree(p->sgmtab2); p->bytes -= p->tab_bytes; }
 	for (int i = 0; i < p->ntm;)                       // forget the maps of the released buffers
 		if (p->tm_ptr[i] == p->bufA2 || p->tm_ptr[i] == p->bufC2) {
 			p->tm_ptr[i] = p->tm_ptr[p->ntm - 1];
@@ -247,7 +261,7 @@ extern "C" int mccnn_pipeline_set_overlap(mccnn_pipeline *p, int mode)
 		int rc = 0, lo = 0, hi = 0;
 		if (!rc) rc = dev_alloc((void **)&p->bufA2, p->V * f, &p->bytes);
 		if (!rc) rc = dev_alloc((void **)&p->bufC2, p->V * f, &p->bytes);
-		if (!rc) rc = dev_alloc((void **)&p->sgmtab2, adc_sgm_dhw_table_bytes(p->H, p->W, p->D), &p->bytes);
+		if (!rc) rc = dev_alloc((void **)&p->sgmtab2, p->tab_bytes, &p->bytes);
 		if (!rc) rc = add_tensor_map(p, p->bufA2);
 		if (!rc) rc = add_tensor_map(p, p->bufC2);
 		if (!rc) rc = (int)cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
@@ -340,11 +354,19 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 			STEP((int)cudaEventRecord(p->ev_hi_in[k], ds));
 			STEP((int)cudaStreamWaitEvent(ss, p->ev_hi_in[k], 0));
 		}
-		for (int it = 0; it < o.sgm_i; it++) {                                                   // :1008-1020, no permutes: (D,H,ld) scans
-			STEP(adc_sgm2_dhw(imgL, imgR, cur, acc, tab, H, W, ld, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
-					  o.sgm_q1, o.sgm_q2, direction, /*div4=*/true, ss));                  // :1014-1016, :1020
-			float *t = cur; cur = acc; acc = t;
-			nl += 5;
+		for (int it = 0; it < o.sgm_i; it++) {                                                   // :1008-1020
+			if (p->sgm_dhw) {                                                                    // no permutes: (D,H,ld) scans
+				STEP(adc_sgm2_dhw(imgL, imgR, cur, acc, tab, H, W, ld, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
+						  o.sgm_q1, o.sgm_q2, direction, /*div4=*/true, ss));              // :1014-1016, :1020
+				float *t = cur; cur = acc; acc = t;
+				nl += 5;
+			} else {
+				STEP(adc_transpose_dhw_pitched_to_hwd(cur, spare, D, H, W, ld, ss));             // :1008
+				STEP(adc_sgm2(imgL, imgR, spare, acc, tab, H, W, D, o.pi1, o.pi2, o.tau_so, o.alpha1,
+					      o.sgm_q1, o.sgm_q2, direction, /*zero_out=*/true, ss));                // :1014-1016
+				STEP(adc_transpose_hwd_to_dhw_pitched_div4(acc, cur, D, H, W, ld, ss));          // :1017-1020
+				nl += 7;
+			}
 		}
 		if (ss != ds) {
 			STEP((int)cudaEventRecord(p->ev_hi_out[k], ss));

@@ -442,6 +442,79 @@ transpose64_kernel(const float *__restrict__ in, float *__restrict__ out, long R
 	}
 }
 
+// Batched tile transpose between a pitched (D, H, ld) volume and the reference's (H, W, D) SGM layout, one image row
+// y = blockIdx.z per grid plane:  B[c][r] = A[r][c] (x scale), A[r][c] = in[r * in_rs + y * in_ys + c],
+// B[c][r] = out[c * out_rs + y * out_ys + r].  64 x 64 tiles, float4 on both sides when VEC (the contiguous extents are
+// multiples of 4 or padded to it: a pitched row may be read / written up to its pitch).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+transpose_rows_kernel(const float *__restrict__ in, float *__restrict__ out, int R, int Cn, int Rlim, int Clim,
+		      long in_rs, long in_ys, long out_rs, long out_ys, float scale)
+{
+	__shared__ float t[64][65];
+	const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+	const long y = blockIdx.z;
+	const int tid = threadIdx.x;
+	in += y * in_ys;
+	out += y * out_ys;
+	if (VEC) {
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const int idx = tid + 256 * i, row = idx >> 4, c4 = (idx & 15) * 4;
+			if (r0 + row < R && c0 + c4 < Clim) {
+				const float4 v = *reinterpret_cast<const float4 *>(in + (long)(r0 + row) * in_rs + c0 + c4);
+				t[row][c4] = v.x; t[row][c4 + 1] = v.y; t[row][c4 + 2] = v.z; t[row][c4 + 3] = v.w;
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const int idx = tid + 256 * i, c = idx >> 4, r4 = (idx & 15) * 4;
+			if (c0 + c < Cn && r0 + r4 < Rlim) {
+				float4 v = make_float4(t[r4][c], t[r4 + 1][c], t[r4 + 2][c], t[r4 + 3][c]);
+				v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+				*reinterpret_cast<float4 *>(out + (long)(c0 + c) * out_rs + r0 + r4) = v;
+			}
+		}
+	} else {
+		for (int i = tid; i < 64 * 64; i += 256) {
+			const int row = i >> 6, c = i & 63;
+			if (r0 + row < R && c0 + c < Cn) t[row][c] = in[(long)(r0 + row) * in_rs + c0 + c];
+		}
+		__syncthreads();
+		for (int i = tid; i < 64 * 64; i += 256) {
+			const int c = i >> 6, r = i & 63;
+			if (c0 + c < Cn && r0 + r < R) out[(long)(c0 + c) * out_rs + r0 + r] = t[r][c] * scale;
+		}
+	}
+}
+
+// (D, H, ld) -> (H, W, D)   main.lua:1008 on the pipeline's pitched volumes
+int adc_transpose_dhw_pitched_to_hwd(const float *in, float *out, int D, int H, int W, int ld, cudaStream_t s)
+{
+	if (H > 65535) return ADCENSUS_ELIMIT;
+	const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
+	dim3 grid(adc_div_up(W, 64), adc_div_up(D, 64), H);
+	const int clim = vec ? ((W + 3) & ~3) : W;     // reads may run into the row padding
+	if (vec) transpose_rows_kernel<true><<<grid, 256, 0, s>>>(in, out, D, W, D, clim, (long)H * ld, ld, D, (long)W * D, 1.0f);
+	else transpose_rows_kernel<false><<<grid, 256, 0, s>>>(in, out, D, W, D, W, (long)H * ld, ld, D, (long)W * D, 1.0f);
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+// (H, W, D) -> (D, H, ld), x 1/4   main.lua:1017-1020 (x * 0.25f is exactly x / 4)
+int adc_transpose_hwd_to_dhw_pitched_div4(const float *in, float *out, int D, int H, int W, int ld, cudaStream_t s)
+{
+	if (H > 65535) return ADCENSUS_ELIMIT;
+	const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ld >= ((W + 3) & ~3) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
+	dim3 grid(adc_div_up(D, 64), adc_div_up(W, 64), H);
+	const int rlim = vec ? ((W + 3) & ~3) : W;     // writes may run into the row padding
+	if (vec) transpose_rows_kernel<true><<<grid, 256, 0, s>>>(in, out, W, D, rlim, D, D, (long)W * D, (long)H * ld, ld, 0.25f);
+	else transpose_rows_kernel<false><<<grid, 256, 0, s>>>(in, out, W, D, W, D, D, (long)W * D, (long)H * ld, ld, 0.25f);
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
 int adc_transpose(const float *in, float *out, long R, long Cn, float div, bool do_div, cudaStream_t s)
 {
 	const bool vec = (R % 4 == 0) && (Cn % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);

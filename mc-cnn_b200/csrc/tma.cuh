@@ -61,7 +61,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 	}
 }
 
-// box of a rank-3 tensor -> shared memory, completion counted in bytes on `bar`
+// box of a rank-3 tensor -> shared memory, completion counted in bytes on `bar`.  c0 (innermost coordinate) must be a
+// multiple of 16 bytes / element size (measured: any other start raises 'illegal instruction'), smem_dst 128-byte aligned
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
 {
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -76,6 +77,18 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
 		     : "r"(tma_smem_addr(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(tma_smem_addr(bar))
 		     : "memory");
 }
+// shared memory -> box of a rank-3 tensor (bulk async-group completion); same alignment rules as the loads
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2)
+{
+	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+		     :
+		     : "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(tma_smem_addr(smem_src))
+		     : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory (the buffer may be reused / the CTA may exit)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
 {
 	asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");

@@ -1,5 +1,8 @@
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_sgm_dhw.py -m gpu -q 2>&1 | tail -25 | tee gpurun_out/r2_c3_sgm_dhw.log
-timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_cbca_tma.py -m gpu -q -x -k "70-300-36-5-0.13--1" > gpurun_out/r2_c3_sanitizer.log 2>&1
-grep -E "=========" gpurun_out/r2_c3_sanitizer.log | head -40
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 | tee gpurun_out/r2_c6_tests.log
+timeout 120 python tools/time_pipeline.py 2>&1 | tail -1
+timeout 120 python tools/time_pipeline.py --overlap 0 2>&1 | tail -1
+timeout 120 python tools/time_pipeline.py --exact 2>&1 | tail -1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:cbca_tma -c 1 -s 4 -f -o gpurun_out/r2_c6_cbca_tma python tools/time_cbca.py --iters 1 > /dev/null 2>&1
+ls -la gpurun_out/*.ncu-rep
