@@ -162,18 +162,28 @@ def make_inputs(cfg, n_pairs, seed0):
 
 
 def algorithmic_bytes(cfg):
+    """algorithmic bytes per launch of each kernel of the step"""
     H, W, D, C = cfg["H"], cfg["W"], cfg["D"], cfg["C"]
     V = 4 * D * H * W
     F = 4 * C * H * W
     valid = 4 * H * (D * W - D * (D - 1) // 2)
     return {
-        "StereoJoin": 2 * F + 2 * valid,          # SURVEY.md 8d
-        "cbca": 2 * V + 32 * H * W,               # per iteration
-        "sgm2": 11 * V,                           # documented 4-pass design: 4 x (read in + RMW out) - 1 read
-        "transpose": 2 * V,
+        "StereoJoin": 2 * F + 2 * valid,
+        "cbca_fast": 2 * V + 32 * H * W,          # per iteration: read V + write V + both images' arms
+        "cbca_exact": 2 * V + 32 * H * W,
+        "sgm2": 11 * V,                           # documented 4-sweep design: 4 x (read in + RMW out) - 1 read of the zero accumulator
+        "transpose_in": 2 * V,
+        "transpose_out": 2 * V,
         "argmin": V + 4 * H * W,
-        "fill_nan": 2 * V,
     }
+
+
+def make_config(cfg):
+    """`config` of the JSON line: IDENTICAL keys and values in both arms (own, reference)"""
+    return {"workload": cfg["name"], "H": cfg["H"], "W": cfg["W"], "D": cfg["D"], "C": cfg["C"], "preset": cfg.get("desc", ""),
+            "pairs_per_gpu_per_step": 1, "parallelism": "pairs sharded over GPUs, one process per GPU, no collective",
+            "l2": "per-step working set (0.23 GB features + >1.6 GB volumes) exceeds the 126 MB L2; single-kernel timings flush L2 "
+                  "with a 256 MB write"}
 
 
 def time_op(fn, iters, flush):
@@ -194,48 +204,65 @@ def time_op(fn, iters, flush):
 
 
 def stage_table(cfg, opt, dev_in, iters=5):
-    """per-operator timings at the bench workload through the op-level C ABI (isolated, L2 flushed)"""
+    """per-kernel timings at the bench workload through the C ABI, each kernel alone on the stream, L2 flushed, on the
+    data layouts the fused pipeline runs them on (pitched (D,H,ld) volumes)"""
     import torch
 
     from mccnn_b200 import adcensus
 
     H, W, D, C = cfg["H"], cfg["W"], cfg["D"], cfg["C"]
+    ld = (W + 3) // 4 * 4
     dev = dev_in["featL"].device
     flushbuf = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     flush = lambda: flushbuf.fill_(1.0)
+    lib = adcensus.lib()
+    lib.mccnn_packed_arms_bytes.restype = ctypes.c_size_t
+    lib.mccnn_packed_hv_bytes.restype = ctypes.c_size_t
+    vp = lambda t_: ctypes.c_void_p(t_.data_ptr())
     fL, fR = dev_in["featL"][None], dev_in["featR"][None]
     iL, iR = dev_in["imgL"][None], dev_in["imgR"][None]
-    vols = torch.empty((2, D, H, W), device=dev)
-    adcensus.fill_nan(vols)
+    st = adcensus._stream(fL)
     t = {}
-    t["fill_nan"] = time_op(lambda: adcensus.fill_nan(vols), iters, flush)
+    # StereoJoin: the operator on contiguous outputs (the pipeline launches the same kernel with the row pitch ld)
+    vols = torch.full((2, D, H, W), float("nan"), device=dev)
     t["StereoJoin"] = time_op(lambda: adcensus.StereoJoin(fL, fR, vols[0:1], vols[1:2]), iters, flush)
     x0c = torch.empty((1, 4, H, W), device=dev); x1c = torch.empty((1, 4, H, W), device=dev)
     t["cross"] = time_op(lambda: adcensus.cross(iL, x0c, opt.L1, opt.tau1), iters, flush)
     adcensus.cross(iR, x1c, opt.L1, opt.tau1)
-    tmp = torch.empty((1, D, H, W), device=dev)
-    # arms packed once (as the pipeline does), so that the timed launch is the aggregation kernel alone
-    lib = adcensus.lib()
-    lib.mccnn_packed_arms_bytes.restype = ctypes.c_size_t
-    packed = torch.empty(lib.mccnn_packed_arms_bytes(H, W), dtype=torch.uint8, device=dev)
-    vp = lambda t_: ctypes.c_void_p(t_.data_ptr())
-    assert lib.mccnn_pack_arms(vp(x0c), vp(x1c), vp(packed), H, W, adcensus._stream(x0c)) == 0
-    t["cbca"] = time_op(lambda: lib.mccnn_cbca_packed(vp(packed), vp(x0c), vp(x1c), vp(vols[0:1]), vp(tmp), D, H, W, -1,
-                                                       max(opt.L1, 2), adcensus._stream(tmp)), iters, flush)
-    volt = adcensus.transpose_dhw_to_hwd(vols[0:1])
-    t["transpose"] = time_op(lambda: adcensus.lib().mccnn_transpose_dhw_to_hwd(
-        adcensus._t(vols[0:1], 1, "t"), adcensus._t(volt, 2, "t"), D, H, W, adcensus._stream(volt)), iters, flush)
+    maxarm = max(opt.L1, 2)
+    # pitched copy of the left volume
+    pin = torch.empty((D, H, ld), device=dev)
+    pin[:, :, :W] = vols[0]
+    pout = torch.empty_like(pin)
+    if opt.cbca_i1 + opt.cbca_i2 > 0:
+        hv = torch.empty(lib.mccnn_packed_hv_bytes(H, W), dtype=torch.uint8, device=dev)
+        assert lib.mccnn_pack_arms_hv(vp(x0c), vp(x1c), vp(hv), H, W, st) == 0
+        t["cbca_fast"] = time_op(lambda: lib.mccnn_cbca_fast_pitched_packed(vp(hv), vp(pin), vp(pout), D, H, W, ld, -1, maxarm, st), iters, flush)
+        packed = torch.empty(lib.mccnn_packed_arms_bytes(H, W), dtype=torch.uint8, device=dev)
+        assert lib.mccnn_pack_arms(vp(x0c), vp(x1c), vp(packed), H, W, st) == 0
+        tmp = torch.empty((1, D, H, W), device=dev)
+        t["cbca_exact"] = time_op(lambda: lib.mccnn_cbca_packed(vp(packed), vp(x0c), vp(x1c), vp(vols[0:1]), vp(tmp), D, H, W, -1, maxarm, st),
+                                  iters, flush)
+    volt = torch.empty((1, H, W, D), device=dev)
+    t["transpose_in"] = time_op(lambda: lib.mccnn_transpose_dhw_pitched_to_hwd(vp(pin), vp(volt), D, H, W, ld, st), iters, flush)
     out = torch.zeros_like(volt)
-    t["sgm2"] = time_op(lambda: adcensus.sgm2(iL, iR, volt, out, None, opt.pi1, opt.pi2, opt.tau_so, opt.alpha1,
-                                             opt.sgm_q1, opt.sgm_q2, -1), iters, flush)
-    t["argmin"] = time_op(lambda: adcensus.argmin(tmp), iters, flush)
-    d = adcensus.argmin(tmp)
+
+    def sgm():
+        out.zero_()
+        adcensus.sgm2(iL, iR, volt, out, None, opt.pi1, opt.pi2, opt.tau_so, opt.alpha1, opt.sgm_q1, opt.sgm_q2, -1)
+
+    t_zero = time_op(lambda: out.zero_(), iters, flush)
+    t["sgm2"] = time_op(sgm, iters, flush) - t_zero
+    t["transpose_out"] = time_op(lambda: lib.mccnn_transpose_hwd_to_dhw_pitched_div4(vp(out), vp(pout), D, H, W, ld, st), iters, flush)
+    dmap = torch.empty((1, 1, H, W), device=dev)
+    t["argmin"] = time_op(lambda: lib.mccnn_argmin_pitched(vp(pout), vp(dmap), D, H, W, ld, st), iters, flush)
+    d = adcensus.argmin(vols[0:1])
     d1 = adcensus.argmin(vols[1:2])
     outl = torch.zeros_like(d)
     t["outlier_detection"] = time_op(lambda: adcensus.outlier_detection(d, d1, outl, D), iters, flush)
     t["interpolate_occlusion"] = time_op(lambda: adcensus.interpolate_occlusion(d, outl), iters, flush)
     t["interpolate_mismatch"] = time_op(lambda: adcensus.interpolate_mismatch(d, outl), iters, flush)
-    t["subpixel"] = time_op(lambda: adcensus.subpixel_enchancement(d, tmp, D), iters, flush)
+    t["subpixel"] = time_op(lambda: adcensus.subpixel_enchancement(d, vols[0:1], D), iters, flush)
     t["median2d"] = time_op(lambda: adcensus.median2d(d, 5), iters, flush)
     kern = adcensus.gaussian(opt.blur_sigma).to(dev)
     t["mean2d"] = time_op(lambda: adcensus.mean2d(d, kern, opt.blur_t), iters, flush)
@@ -263,6 +290,38 @@ def cpu_baseline(cfg, opt):
                 rows - 1, cfg["H"], cfg["W"], cfg["D"], 100 * frac, dt)}
 
 
+def timed_steps(sp, dev_in, disp, K, warm, world, sample_clocks=None):
+    """K timed steps (one pair per step) of the fused pipeline, barrier + synchronize on both sides; max over ranks (ms)"""
+    import torch
+
+    for i in range(warm):
+        x = dev_in[i % 2]
+        sp.run(x["featL"], x["featR"], x["imgL"], x["imgR"], disp=disp)
+    barrier_sync(world)
+    if sample_clocks is not None:
+        sample_clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        x = dev_in[i % 2]
+        sp.run(x["featL"], x["featR"], x["imgL"], x["imgR"], disp=disp)
+    e1.record()
+    barrier_sync(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)
+
+
+def load_traffic(workload):
+    """DRAM bytes per launch (dram__bytes_read + write) of the kernels of this workload from the committed ncu launch list
+    of the same pipeline (profiles/r2_traffic_<workload>.json, written by tools/launch_summary.py --json)"""
+    p = os.path.join(ROOT, "profiles", "r2_traffic_%s.json" % workload)
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), os.path.relpath(p, ROOT)
+        except Exception:
+            pass
+    return {}, None
+
+
 def run_b200(args):
     import torch
 
@@ -286,45 +345,22 @@ def run_b200(args):
     disp = torch.empty((cfg["H"], cfg["W"]), device=dev)
     K, Wm = args.steps, max(args.warmup, 3)
 
-    # ---- device-resident throughput -------------------------------------------------------
-    for i in range(Wm):
-        x = dev_in[i % 2]
-        sp.run(x["featL"], x["featR"], x["imgL"], x["imgR"], disp=disp)
-    barrier_sync(world)
+    # ---- device-resident throughput, default mode (constant-work CBCA, 1e-4 contract) ---------------
     sampler = ClockSampler(local)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        x = dev_in[i % 2]
-        sp.run(x["featL"], x["featR"], x["imgL"], x["imgR"], disp=disp)
-    e1.record()
-    barrier_sync(world)
-    ms_total = max_over_ranks(e0.elapsed_time(e1), world)
+    assert sp.cbca_mode == "fast"
+    ms_total = timed_steps(sp, dev_in, disp, K, Wm, world, sampler)
     clocks = sampler.stop()
     launches = sp.launches_per_run * K
-
-    # ---- same, with the opt-in approximate CBCA (NOT bit-exact; reported beside the headline) ----
-    sp.set_fast_cbca(True)
-    for i in range(2):
-        x = dev_in[i % 2]
-        sp.run(x["featL"], x["featR"], x["imgL"], x["imgR"], disp=disp)
-    barrier_sync(world)
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(K):
-        x = dev_in[i % 2]
-        sp.run(x["featL"], x["featR"], x["imgL"], x["imgR"], disp=disp)
-    f1.record()
-    barrier_sync(world)
-    ms_fast = max_over_ranks(f0.elapsed_time(f1), world)
     disp_fast = disp.clone()
-    sp.set_fast_cbca(False)
-    sp.run(dev_in[(K - 1) % 2]["featL"], dev_in[(K - 1) % 2]["featR"], dev_in[(K - 1) % 2]["imgL"], dev_in[(K - 1) % 2]["imgR"], disp=disp)
-    torch.cuda.synchronize()
-    fast_diff_frac = float(((disp_fast - disp).abs() > 1e-4 * disp.abs().clamp(min=1.0)).float().mean().item())
 
-    # ---- end to end through the host-buffer C-ABI call --------------------------------------
+    # ---- same steps in the exact mode (every output bit-identical to the reference) --------------------
+    sp.set_cbca_mode("exact")
+    ms_exact = timed_steps(sp, dev_in, disp, K, 2, world)
+    # SURVEY.md 8(d) fast-mode bar on disp.bin: <= 1e-4 on >= (1 - 1e-4) of the pixels
+    fast_diff_frac = float(((disp_fast - disp).abs() > 1e-4 * disp.abs().clamp(min=1.0)).float().mean().item())
+    sp.set_cbca_mode("fast")
+
+    # ---- end to end through the host-buffer C-ABI call (default mode) --------------------------------------
     # one batch call per timed region: every step's inputs cross PCIe from pinned host memory and every
     # step's disparity map comes back; copies of neighbouring steps overlap the kernels (3 streams)
     host_pairs = [tuple(pairs[i % 2][k] for k in ("featL", "featR", "imgL", "imgR")) for i in range(K)]
@@ -343,55 +379,79 @@ def run_b200(args):
     F = 4 * cfg["C"] * cfg["H"] * cfg["W"]
     I = 4 * cfg["H"] * cfg["W"]
 
-    # ---- per-stage timings + roofline of the dominant kernel (rank 0) -------------------------
+    # ---- rank 0: the unchanged-main.lua path, per-kernel timings, rooflines ------------------------------------
     out = None
     if rank == 0:
+        # op chain: main.lua:929-1082 through the adcensus.* operators one by one (what an unpatched main.lua drives
+        # through the Lua face): fill, StereoJoin, cross/cbca with vol:copy, permutes, sgm2, argmin, post
+        xb = torch.stack([dev_in[0]["imgL"], dev_in[0]["imgR"]])[:, None].contiguous()
+        ft = torch.stack([dev_in[0]["featL"], dev_in[0]["featR"]]).contiguous()
+        pipeline.stereo_predict(xb, ft, opt, cfg["D"])
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_chain = 3
+        c0.record()
+        for _ in range(n_chain):
+            pipeline.stereo_predict(xb, ft, opt, cfg["D"])
+        c1.record()
+        torch.cuda.synchronize()
+        chain_ms = c0.elapsed_time(c1) / n_chain
+        del xb, ft
+
         stages = stage_table(cfg, opt, dev_in[0], iters=max(3, min(K, 10)))
         if args.stages:
             for k, v in stages.items():
                 sys.stderr.write("%-24s %8.3f ms\n" % (k, v))
         ab = algorithmic_bytes(cfg)
         n_cbca = 2 * (opt.cbca_i1 + opt.cbca_i2)
-        share = {"StereoJoin": stages["StereoJoin"], "cbca": n_cbca * stages["cbca"], "sgm2": 2 * opt.sgm_i * stages["sgm2"],
-                 "transpose": 4 * stages["transpose"], "argmin": 2 * stages["argmin"], "fill_nan": stages["fill_nan"]}
-        dom = max(share, key=share.get)
         peak, peak_src = load_peaks()
-
-        traffic = {}
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic_k228.json")
-        if args.workload == "k228" and not args.small and os.path.exists(tpath):
-            traffic = json.load(open(tpath))
+        traffic, traffic_src = load_traffic(args.workload if not args.small else "none")
 
         def roof(name):
             ach = ab[name] / (stages[name] * 1e-3) / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": traffic.get(name), "peak_source": peak_src,
+                    "frac": round(ach / peak, 4), "traffic": traffic.get(name), "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes": ab[name], "ms": round(stages[name], 4)}
 
+        def shares(cb):
+            sh = {"StereoJoin": stages["StereoJoin"], "sgm2": 2 * opt.sgm_i * stages["sgm2"],
+                  "transpose_in": 2 * opt.sgm_i * stages["transpose_in"], "transpose_out": 2 * opt.sgm_i * stages["transpose_out"],
+                  "argmin": 2 * stages["argmin"]}
+            if n_cbca:
+                sh[cb] = n_cbca * stages[cb]
+            return sh
+
+        sh_fast, sh_exact = shares("cbca_fast"), shares("cbca_exact")
+        dom_fast, dom_exact = max(sh_fast, key=sh_fast.get), max(sh_exact, key=sh_exact.get)
         out = {
             "metric": "stereo pairs/sec (370x1226 d=%d)" % cfg["D"], "value": round(world * K / (ms_total * 1e-3), 3),
             "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_total / K, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "H": cfg["H"], "W": cfg["W"], "D": cfg["D"], "C": cfg["C"],
-                       "preset": cfg.get("desc", ""),
-                       "pairs_per_gpu_per_step": 1, "parallelism": "pairs sharded over GPUs, no collective",
-                       "schedule": "the two directions of a pair overlapped on two streams (mccnn_pipeline_set_overlap mode 2)",
-                       "l2": "per-step working set (0.23 GB features + 1.65 GB volumes) exceeds the 126 MB L2; "
-                             "stage timings flush L2 with a 256 MB write"},
+            "config": make_config(cfg),
+            "mode": "default: constant-work CBCA (float aggregation within the north star's 1e-4 of the reference, measured ~1e-6; index "
+                    "work bit-exact given the volumes); the exact mode (every output bit-identical) is reported under modes.exact",
+            "schedule": "the two directions of a pair overlapped on two streams (mccnn_pipeline_set_overlap mode 2)",
             "clocks": clocks,
             "e2e": {"value": round(world * K / e2e_s, 3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * F + 2 * I,
                     "d2h_bytes_per_step": I, "api": "mccnn_pipeline_run_host_batch (host buffers in, host disparity maps out)",
                     "single_pair_latency_ms": round(e2e_single_ms, 3)},
             "gpu_launches": launches,
-            "fast_cbca": {"value": round(world * K / (ms_fast * 1e-3), 3), "unit": "pairs/s", "ms_per_step": round(ms_fast / K, 4),
-                          "note": "opt-in prefix-sum CBCA (mccnn_pipeline_set_fast_cbca): volumes within ~1e-6 relative of the "
-                                  "exact mode, not bit-exact; the headline `value` uses the exact mode",
-                          "disp_pixels_differing_from_exact_frac": fast_diff_frac},
-            "roofline": roof(dom),
+            "roofline": roof(dom_fast),
+            "modes": {
+                "fast": {"value": round(world * K / (ms_total * 1e-3), 3), "unit": "pairs/s", "ms_per_step": round(ms_total / K, 4),
+                         "roofline": roof(dom_fast), "step_share_ms": {k: round(v, 4) for k, v in sh_fast.items()},
+                         "disp_pixels_off_by_more_than_1e-4_vs_exact_frac": fast_diff_frac},
+                "exact": {"value": round(world * K / (ms_exact * 1e-3), 3), "unit": "pairs/s", "ms_per_step": round(ms_exact / K, 4),
+                          "roofline": roof(dom_exact), "step_share_ms": {k: round(v, 4) for k, v in sh_exact.items()}},
+            },
             "roofline_stereojoin": roof("StereoJoin"),
-            "roofline_cbca": roof("cbca"),
+            "roofline_cbca": roof("cbca_fast") if n_cbca else None,
+            "roofline_cbca_exact": roof("cbca_exact") if n_cbca else None,
+            "roofline_sgm2": roof("sgm2"),
+            "op_chain": {"value": round(1e3 / chain_ms, 3), "unit": "pairs/s", "ms_per_pair": round(chain_ms, 3), "n_gpus": 1,
+                         "note": "unchanged-main.lua path: adcensus.* operators one by one (exact kernels, Lua-side fill / copy / permute "
+                                 "steps included), device-resident, rank 0"},
             "stage_ms": {k: round(v, 4) for k, v in stages.items()},
-            "step_share_ms": {k: round(v, 4) for k, v in share.items()},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(cfg, opt)
@@ -406,58 +466,68 @@ def run_b200(args):
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return  # rank 0 alone runs the reference arm
+    """The reference's own implementation of the path: adcensus.cu compiled unmodified (oracle/_ref), driven in main.lua's
+    order.  It is a GPU implementation (the reference has no CPU path), so under torchrun every rank drives it on its
+    own GPU -- like rgs.py:9-14 runs one process per GPU -- and rank 0 prints the aggregate."""
     from oracle import refdriver
 
+    rank = int(os.environ.get("RANK", "0"))
     if not os.path.exists(refdriver.REF_LIB):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libadcensus_ref.so missing (reference tree was not present at build time)"}))
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libadcensus_ref.so missing (reference tree was not present at build time)"}))
         return
-    import numpy as np
     import torch
 
     import mccnn_b200  # noqa: F401
     from mccnn_b200 import pipeline
 
-    torch.cuda.set_device(0)
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    rank, world, local = dist_setup(args)
     cfg = dict(WORKLOADS[args.workload])
     if args.small:
         cfg.update(name="debug_small", H=64, W=128, D=16)
     opt = pipeline.make_params(*cfg["preset"])
-    dev = torch.device("cuda", 0)
-    pairs = make_inputs(cfg, 2, 1000)
+    dev = torch.device("cuda", local)
+    pairs = make_inputs(cfg, 2, 1000 + 16 * rank)
     shim = refdriver.ShimLibrary(refdriver.REF_LIB)
     xb = [torch.stack([p["imgL"], p["imgR"]])[:, None].to(dev) for p in pairs]
     ft = [torch.stack([p["featL"], p["featR"]]).to(dev) for p in pairs]
     K, Wm = args.steps, max(args.warmup, 1)
     for i in range(Wm):
         refdriver.stereo_predict(shim, xb[i % 2], ft[i % 2], opt, cfg["D"])
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
+    barrier_sync(world)
+    sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
         refdriver.stereo_predict(shim, xb[i % 2], ft[i % 2], opt, cfg["D"])
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    barrier_sync(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
     clocks = sampler.stop()
-    v = round(K / (ms * 1e-3), 4)
-    print(json.dumps({
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    v = round(world * K / (ms * 1e-3), 4)
+    os.write(json_fd, (json.dumps({
         "impl": "reference", "metric": "stereo pairs/sec (370x1226 d=%d)" % cfg["D"], "value": v, "unit": "pairs/s",
-        "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 3), "higher_is_better": True,
+        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "H": cfg["H"], "W": cfg["W"], "D": cfg["D"], "C": cfg["C"],
-                   "note": "reference adcensus.cu compiled unmodified for sm_100a (oracle/_ref), driven in main.lua:929-1082 "
-                           "order with torch ops for the cutorch-side fill/copy/transpose/div; the reference has no CPU path, "
-                           "so its own implementation of the path is this GPU one (1 B200, rank 0)"},
+        "config": make_config(cfg),
+        "note": "reference adcensus.cu compiled unmodified for sm_100a (oracle/_ref), driven in main.lua:929-1082 order with torch ops "
+                "for the cutorch-side fill/copy/transpose/div; the reference has no CPU path, so its own implementation of the path is "
+                "this GPU one, one process per GPU like rgs.py",
         "clocks": clocks,
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": 0, "kind": "reference",
-                         "sample": "%d full pairs on one B200 (CUDA reference; host cores only launch)" % K},
+                         "sample": "%d full pairs per GPU on %d B200 (CUDA reference; host cores only launch)" % (K, world)},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }) + "\n").encode())
 
 
 if __name__ == "__main__":

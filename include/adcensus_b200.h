@@ -55,6 +55,13 @@ const char *adcensus_version(void);
 int adcensus_StereoJoin(const float *input_L, const float *input_R, float *output_L, float *output_R,
 			int C, int D, int H, int W, adcensus_stream_t stream);
 
+/* StereoJoin into PITCHED volumes (D, H, ld), ld % 4 == 0, 16-byte aligned outputs, W even, 8-byte aligned features (else
+ * ADCENSUS_EINVAL): 8-byte cp.async operand loads, the left volume leaves through one TMA store per tile.  Same
+ * values as adcensus_StereoJoin bit for bit; additionally output_L[d,y,x] = NaN for x < d (the fill of main.lua:946 for
+ * the left volume); output_R's entries with x >= W - d are left untouched. */
+int mccnn_stereo_join_pitched(const float *input_L, const float *input_R, float *output_L, float *output_R,
+			      int C, int D, int H, int W, int ld, adcensus_stream_t stream);
+
 /* adcensus.cross(x0, out, L1, tau1)  adcensus.cu:280-341; out is (4,H,W) */
 int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1, adcensus_stream_t stream);
 
@@ -88,6 +95,12 @@ int mccnn_cbca_packed(const void *packed, const float *x0c, const float *x1c, co
 int mccnn_cbca_fast_pitched(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 			    int D, int H, int W, int ld, int direction, int max_arm, adcensus_stream_t stream);
 
+/* The two halves of mccnn_cbca_fast_pitched: pack both arm tensors once (mccnn_packed_hv_bytes(H, W) bytes), then iterate. */
+size_t mccnn_packed_hv_bytes(int H, int W);
+int mccnn_pack_arms_hv(const float *x0c, const float *x1c, void *hv, int H, int W, adcensus_stream_t stream);
+int mccnn_cbca_fast_pitched_packed(const void *hv, const float *vol_in, float *vol_out,
+				   int D, int H, int W, int ld, int direction, int max_arm, adcensus_stream_t stream);
+
 /* adcensus.sgm2(x0, x1, input, output, tmp, pi1, pi2, tau_so, alpha1, sgm_q1,
  *               sgm_q2, direction)  adcensus.cu:535-697
  * input/output are (H,W,D); output is accumulated into (+=) in the order right,
@@ -114,6 +127,22 @@ int mccnn_sgm2_band(const float *x0, const float *x1, const float *input, float 
 		    int H, int W, int D, int Ht, int Wt, int yoff, int xoff,
 		    float pi1, float pi2, float tau_so, float alpha1, float sgm_q1, float sgm_q2,
 		    int direction, int pass_mask, int zero_out, adcensus_stream_t stream);
+
+/* Wavefront split of sgm2 over ROW bands (the multi-GPU single-volume path, rowband.py).  Build the penalty-class tables
+ * of the image pair once (mccnn_sgm_tables_bytes bytes; classes + the selector words of one `direction`), then run the
+ * passes band by band on (H,W,D) band volumes at image row offset yoff: horizontal passes (bits 0-1) are band-local; a
+ * vertical pass (bit 2 down or bit 3 up, ONE per call when chained) over the columns [xa, xb) takes the line state of the
+ * row before the band from state_in (NULL only where the scan starts at the image border) and leaves the state of the
+ * band's last row in state_out: [W][mccnn_sgm_state_pitch(D)] floats.  Same arithmetic and accumulation order as
+ * adcensus_sgm2: chained over all bands the result is bit-identical to the whole-image call. */
+size_t mccnn_sgm_tables_bytes(int Ht, int Wt, int D);
+int mccnn_sgm_state_pitch(int D);
+int mccnn_sgm_tables_build(const float *x0, const float *x1, void *tab, int Ht, int Wt, int D, float tau_so,
+			   int direction, adcensus_stream_t stream);
+int mccnn_sgm2_rows(const void *tab, const float *input, float *output, int H, int W, int D, int Ht, int yoff,
+		    float pi1, float pi2, float tau_so, float alpha1, float sgm_q1, float sgm_q2,
+		    int direction, int pass_mask, int zero_out, int xa, int xb,
+		    const float *state_in, float *state_out, adcensus_stream_t stream);
 
 /* adcensus.outlier_detection(d0, d1, outlier, disp_max)  adcensus.cu:878-918 */
 int adcensus_outlier_detection(const float *d0, const float *d1, float *outlier,
@@ -172,6 +201,11 @@ int mccnn_transpose_hwd_to_dhw_div4(const float *in, float *out, int D, int H, i
 /* _, d = torch.min(vol, 2); d:add(-1)  main.lua:1049-1050: 0-based argmin as float,
  * first minimum, NaN skipped (the in-repo statement is spatial_argmin) */
 int mccnn_argmin(const float *vol, float *disp, int D, int HW, adcensus_stream_t stream);
+/* the same three ops on the fused pipeline's pitched (D, H, ld) volumes: (D,H,ld) -> (H,W,D); (H,W,D) -> (D,H,ld) with /4;
+ * first minimum over D */
+int mccnn_transpose_dhw_pitched_to_hwd(const float *in, float *out, int D, int H, int W, int ld, adcensus_stream_t stream);
+int mccnn_transpose_hwd_to_dhw_pitched_div4(const float *in, float *out, int D, int H, int W, int ld, adcensus_stream_t stream);
+int mccnn_argmin_pitched(const float *vol, float *disp, int D, int H, int W, int ld, adcensus_stream_t stream);
 /* gaussian(sigma)  main.lua:528-540: HOST helper; returns ksize, fills out (ksize*ksize) if non-NULL */
 int mccnn_gaussian(double sigma, float *out_host);
 

@@ -32,7 +32,7 @@
 namespace {
 
 constexpr int CT_TX = 128, CT_TY = 32, CT_NT = 256, CT_HO = CT_TY / 2;
-constexpr int CT_DCH = 12;                 // disparities per CTA (window width)
+constexpr int CT_DCH = 20;                 // disparities per CTA (window width); the per-CTA staging of the arm windows is amortised over them
 constexpr int CT_WW = CT_TX + CT_DCH;      // pitch of the right-image arm windows
 
 template <int R>
@@ -104,17 +104,43 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 			}
 	}
 
-	// right-image arm windows (once per CTA), 0 outside the image
-	for (int i = tid; i < TH * CT_WW; i += CT_NT) {
-		const int r = i / CT_WW, j = i - r * CT_WW;
-		const int yy = y0 - HALO + r, xx = a1x0 + j;
-		winH[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(a1h + (long)yy * W + xx) : 0u;
-	}
-	for (int i = tid; i < CT_TY * CT_WW; i += CT_NT) {
-		const int r = i / CT_WW, j = i - r * CT_WW;
-		const int yy = y0 + r, xx = a1x0 + j;
-		const uint32_t v = (yy < H && xx >= 0 && xx < W) ? __ldg(a1v + (long)yy * W + xx) : 0u;
-		winV[i] = (uint16_t)(((v >> 8) & 255u) | ((v >> 16) & 0xff00u));   // U | D << 8
+	// right-image arm windows (once per CTA), 0 outside the image: a warp per window row, lanes along x.  The H words
+	// go straight to shared memory (cp.async, zero-filled outside the image; waited for before the first walk), the V
+	// words are narrowed to U | D << 8 on the way.
+	{
+		const int lane = tid & 31, warp = tid >> 5;
+		constexpr int NW = CT_NT / 32, NCH = (CT_WW + 31) / 32;
+		for (int r = warp; r < TH; r += NW) {
+			const int yy = y0 - HALO + r;
+			const bool rowok = yy >= 0 && yy < H;
+			const uint32_t *grow = a1h + (long)(rowok ? yy : 0) * W;
+#pragma unroll
+			for (int m = 0; m < NCH; m++) {
+				const int j = lane + 32 * m, xx = a1x0 + j;
+				if (j < CT_WW) {
+					const bool ok = rowok && xx >= 0 && xx < W;
+					const unsigned dst = (unsigned)__cvta_generic_to_shared(winH + r * CT_WW + j);
+					const int nbytes = ok ? 4 : 0;
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(grow + (ok ? xx : 0)), "r"(nbytes));
+				}
+			}
+		}
+		asm volatile("cp.async.commit_group;");
+		for (int r = warp; r < CT_TY; r += NW) {
+			const int yy = y0 + r;
+			const uint32_t *grow = a1v + (long)(yy < H ? yy : 0) * W;
+			uint32_t v[NCH];
+#pragma unroll
+			for (int m = 0; m < NCH; m++) {
+				const int xx = a1x0 + lane + 32 * m;
+				v[m] = (yy < H && xx >= 0 && xx < W) ? __ldg(grow + xx) : 0u;
+			}
+#pragma unroll
+			for (int m = 0; m < NCH; m++) {
+				const int j = lane + 32 * m;
+				if (j < CT_WW) winV[r * CT_WW + j] = (uint16_t)(((v[m] >> 8) & 255u) | ((v[m] >> 16) & 0xff00u));   // U | D << 8
+			}
+		}
 	}
 	// this thread's own column of the left image's arms: registers for the whole chunk
 	uint32_t ah[NWALK], av[CT_HO];
@@ -128,7 +154,6 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		const int yy = yb + k;
 		av[k] = (x < W && yy < H) ? __ldg(a0v + (long)yy * W + x) : 0u;
 	}
-	__syncthreads();
 
 	for (int dd = 0; dd < nproc; dd++) {
 		const int d = d0 + dd, s = dd & 1;
@@ -181,6 +206,7 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 				p4[i] = q;
 			}
 		}
+		if (dd == 0) asm volatile("cp.async.wait_group 0;");   // the arm windows of this chunk have landed
 		__syncthreads();
 
 		// 2. column walk: relative row rr <-> tile row 16h + rr <-> image row yb - HALO + rr.
@@ -198,44 +224,71 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		float T = 0.0f;
 		int N = 0;
 		*reinterpret_cast<float2 *>(rgb) = make_float2(0.0f, __int_as_float(0));   // relative row 0: the excluded row of output 0
+		// rows in batches of WB: all the shared-memory reads of a batch are issued before its (short) serial part, so that
+		// their latency overlaps (the kernel is latency-, not bandwidth-bound at 16 warps per SM)
+		constexpr int WB = 4;
 #pragma unroll
-		for (int rr = 1; rr <= NWALK; rr++) {
-			const uint32_t hw = __vminu2(ah[rr - 1], wh[rr * CT_WW]);   // min of lengths = (max of left ends, min of right ends), :362-363
-			const int L4 = hw & 0xffffu, R4 = hw >> 16;
-			const char *pr = Pc + rr * (TWP * 4);
-			const float S = *reinterpret_cast<const float *>(pr + R4) - *reinterpret_cast<const float *>(pr - L4);   // run (x - L, x + R_), :364-367
-			T = fmaf(S, 4.0f, T);
-			N += L4 + R4;                                            // 4 x its length, :368
-			*reinterpret_cast<float2 *>(rgb + (rr & (RING - 1)) * RROW) = make_float2(T, __int_as_float(N));
-			if (rr >= 2 * R + 1) {
-				constexpr int M = RING - 1;
-				const int k = rr - 2 * R - 1;                        // output row yb + k = relative row HALO + k
-				const int rk = HALO + k;
-				const uint32_t vw = __vminu2(av[k], __byte_perm((uint32_t)wv[k * CT_WW], 0u, 0x1404));   // :359-360
-				const int U8 = vw & 0xffffu, D8 = vw >> 16;
-				// rows y - U + 1 .. y + Dn - 1 (:361): T(rk + Dn - 1) - T(rk - U); the ring index wraps only
-				// where the (compile-time) row position says it can
-				int oh = D8 * 8 + (((rk - 1) & M) * RROW);
-				if (((rk - 1) & M) + R + 1 > M) oh &= RMASK;
-				int ol = ((rk & M) * RROW) - U8 * 8;
-				if ((rk & M) - R - 1 < 0) ol = (ol + RING * RROW) & RMASK;
-				const float2 a = *reinterpret_cast<const float2 *>(rgb + oh), b = *reinterpret_cast<const float2 *>(rgb + ol);
-				const float cnt = (float)(__float_as_int(a.y) - __float_as_int(b.y));
-				float rc;
-				asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(cnt));   // count >= 1; 1-ulp reciprocal, inside the 1e-4 contract
-				const float res = (a.x - b.x) * rc;                       // :373
-				asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(po), "f"(res), "r"(k), "r"(nst)
-					     : "memory");
-				po += ldb;
+		for (int b0 = 1; b0 <= NWALK; b0 += WB) {
+			uint32_t hw[WB], vw[WB];
+			float ph[WB], pl[WB];
+#pragma unroll
+			for (int i = 0; i < WB; i++) {
+				const int rr = b0 + i;
+				if (rr <= NWALK) {
+					hw[i] = __vminu2(ah[rr - 1], wh[rr * CT_WW]);   // min of lengths = (max of left ends, min of right ends), :362-363
+					if (rr >= 2 * R + 1) {
+						const int k = rr - 2 * R - 1;
+						vw[i] = __vminu2(av[k], __byte_perm((uint32_t)wv[k * CT_WW], 0u, 0x1404));   // :359-360
+					}
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < WB; i++) {
+				const int rr = b0 + i;
+				if (rr <= NWALK) {
+					const int L4 = hw[i] & 0xffffu, R4 = hw[i] >> 16;
+					const char *pr = Pc + rr * (TWP * 4);
+					ph[i] = *reinterpret_cast<const float *>(pr + R4);
+					pl[i] = *reinterpret_cast<const float *>(pr - L4);
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < WB; i++) {
+				const int rr = b0 + i;
+				if (rr > NWALK) continue;
+				const int L4 = hw[i] & 0xffffu, R4 = hw[i] >> 16;
+				T = fmaf(ph[i] - pl[i], 4.0f, T);                    // + 4 x sum of the run (x - L, x + R_), :364-367
+				N += L4 + R4;                                        // + 4 x its length, :368
+				*reinterpret_cast<float2 *>(rgb + (rr & (RING - 1)) * RROW) = make_float2(T, __int_as_float(N));
+				if (rr >= 2 * R + 1) {
+					constexpr int M = RING - 1;
+					const int k = rr - 2 * R - 1;                    // output row yb + k = relative row HALO + k
+					const int rk = HALO + k;
+					const int U8 = vw[i] & 0xffffu, D8 = vw[i] >> 16;
+					// rows y - U + 1 .. y + Dn - 1 (:361): T(rk + Dn - 1) - T(rk - U); the ring index wraps only
+					// where the (compile-time) row position says it can
+					int oh = D8 * 8 + (((rk - 1) & M) * RROW);
+					if (((rk - 1) & M) + R + 1 > M) oh &= RMASK;
+					int ol = ((rk & M) * RROW) - U8 * 8;
+					if ((rk & M) - R - 1 < 0) ol = (ol + RING * RROW) & RMASK;
+					const float2 a = *reinterpret_cast<const float2 *>(rgb + oh), b = *reinterpret_cast<const float2 *>(rgb + ol);
+					const float cnt = (float)(__float_as_int(a.y) - __float_as_int(b.y));
+					float rc;
+					asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(cnt));   // count >= 1; 1-ulp reciprocal, inside the 1e-4 contract
+					const float res = (a.x - b.x) * rc;                       // :373
+					asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(po), "f"(res), "r"(k), "r"(nst)
+						     : "memory");
+					po += ldb;
+				}
 			}
 		}
 		if (!valid_col && nv > 0) {                        // x + d*direction outside the image: plain copy, keeps NaN (:353-354)
 			const long idx0 = ((long)d * H + yb) * ld + x;
 			for (int k = 0; k < nv; k++) out[idx0 + (long)k * ld] = __ldg(vol + idx0 + (long)k * ld);
 		}
+		fence_proxy_async_smem();                          // generic-proxy accesses (the in-place prefix) before the TMA refill
 		__syncthreads();                                   // every reader of this stage is done
 		if (tid == 0 && dd + 2 < nproc) {
-			fence_proxy_async_smem();                      // generic-proxy writes (the in-place prefix) before the TMA refill
 			mbar_arrive_expect_tx(&bars[s], C::TILE_BYTES);
 			tma_load_3d(P, &tmap, x0 - HX, y0 - HALO, d + 2, &bars[s]);
 		}
@@ -353,4 +406,31 @@ extern "C" int mccnn_cbca_fast_pitched(const float *x0c, const float *x1c, const
 	if (!rc) rc = adc_cbca_tma(&tm, hv, vol_in, vol_out, D, H, W, ld, direction, max_arm - 1, s);
 	int rc2 = adc_scratch_free(hv, s);
 	return rc ? rc : rc2;
+}
+
+// The two halves of mccnn_cbca_fast_pitched for callers that aggregate several times with the same arms (main.lua runs
+// cbca_i1 + cbca_i2 iterations per direction): pack once into `hv` (mccnn_packed_hv_bytes(H, W) bytes), then iterate.
+extern "C" size_t mccnn_packed_hv_bytes(int H, int W) { return adc_packed_hv_words(H, W) * sizeof(uint32_t); }
+
+extern "C" int mccnn_pack_arms_hv(const float *x0c, const float *x1c, void *hv, int H, int W, adcensus_stream_t stream)
+{
+	if (!x0c || !x1c || !hv || H < 1 || W < 1) return ADCENSUS_EINVAL;
+	int rc = adc_pack_arms_hv(x0c, (uint32_t *)hv, 0, H, W, adc_stream(stream));
+	if (!rc) rc = adc_pack_arms_hv(x1c, (uint32_t *)hv, 1, H, W, adc_stream(stream));
+	return rc;
+}
+
+extern "C" int mccnn_cbca_fast_pitched_packed(const void *hv, const float *vol_in, float *vol_out,
+					      int D, int H, int W, int ld, int direction, int max_arm, adcensus_stream_t stream)
+{
+	if (!hv || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
+	if (D < 1 || H < 1 || W < 1 || ld < W || (ld & 3) || (direction != 1 && direction != -1) || max_arm < 1) return ADCENSUS_EINVAL;
+	if ((((uintptr_t)vol_in) | ((uintptr_t)vol_out)) & 15) return ADCENSUS_EINVAL;
+	if (max_arm - 1 > adc_cbca_tma_max_halo()) return ADCENSUS_ELIMIT;
+	CUtensorMap tm;
+	int bw, bh;
+	adc_cbca_tma_box(max_arm - 1, &bw, &bh);
+	int rc = adc_tma_encode_volume(&tm, vol_in, D, H, W, ld, bw, bh);
+	if (rc) return rc;
+	return adc_cbca_tma(&tm, (const uint32_t *)hv, vol_in, vol_out, D, H, W, ld, direction, max_arm - 1, adc_stream(stream));
 }

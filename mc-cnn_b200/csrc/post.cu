@@ -4,7 +4,7 @@
 // Reference: spatial_argmin adcensus.cu:244-278, outlier_detection :878-918,
 // interpolate_occlusion :1079-1125, interpolate_mismatch :1001-1077,
 // subpixel_enchancement :1205-1239, median2d :1575-1613, mean2d :1241-1282,
-// Normalize_forward :1284-1333, ad :62-114, census :117-175; Lua side
+// Normalize_forward :1284-1333 (ad / census live in adcensus_cost.cu); Lua side
 // main.lua:946 (fill), :922-927 (fix_border), :1008/:1020 (permutes), :1049-1050
 // (torch.min).  All of these are bit-exact restatements: index/label work is
 // integer, the float expressions keep the reference's operation order (fmaf where
@@ -295,61 +295,6 @@ __global__ void normalize_kernel(const float *__restrict__ in, float *__restrict
 	for (int c = 0; c < C; c++) dst[(long)c * HW] = src[(long)c * HW] / s; // :1306
 }
 
-// ------------------------------------------------------------------ ad / census
-__global__ void ad_kernel(const float *__restrict__ x0, const float *__restrict__ x1, float *__restrict__ out, long size, int H, int W, int direction)
-{
-	long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (id >= size) return;
-	int x = (int)(id % W), y = (int)((id / W) % H);
-	int d = (int)(id / ((long)H * W)) * direction;
-	float dist;
-	if (0 <= x + d && x + d < W) {
-		int cnt = 0;
-		dist = 0;
-		for (int yy = y - 4; yy <= y + 4; yy++)
-			for (int xx = x - 4; xx <= x + 4; xx++)
-				if (0 <= xx && xx < W && 0 <= xx + d && xx + d < W && 0 <= yy && yy < H) {
-					int ind = yy * W + xx;
-					dist += fabsf(__ldg(x0 + ind) - __ldg(x1 + ind + d));
-					cnt++;
-				}
-		dist /= cnt;
-	} else {
-		dist = adc_nan();
-	}
-	out[id] = dist;
-}
-
-__global__ void census_kernel(const float *__restrict__ x0, const float *__restrict__ x1, float *__restrict__ out, long size, int nch, int H, int W, int direction)
-{
-	long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (id >= size) return;
-	int x = (int)(id % W), y = (int)((id / W) % H);
-	int d = (int)(id / ((long)H * W)) * direction;
-	float dist;
-	if (0 <= x + d && x + d < W) {
-		dist = 0;
-		for (int i = 0; i < nch; i++) {
-			long ip = ((long)i * H + y) * W + x;
-			float p0 = __ldg(x0 + ip), p1 = __ldg(x1 + ip + d);
-			for (int yy = y - 4; yy <= y + 4; yy++)
-				for (int xx = x - 4; xx <= x + 4; xx++) {
-					if (0 <= xx && xx < W && 0 <= xx + d && xx + d < W && 0 <= yy && yy < H) {
-						long iq = ((long)i * H + yy) * W + xx;
-						if ((__ldg(x0 + iq) < p0) != (__ldg(x1 + iq + d) < p1)) dist++;
-					} else {
-						dist++;
-					}
-				}
-		}
-		dist /= nch;
-	} else {
-		dist = adc_nan();
-	}
-	out[id] = dist;
-}
-
-// ------------------------------------------------------------------ Lua-side tensor ops
 __global__ void fill_nan_kernel(float4 *p4, size_t n4, float *tail, int ntail)
 {
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,8 +313,8 @@ __global__ void fill_invalid_kernel(float *volL, float *volR, int D, int H, int 
 	const float q = adc_nan();
 	for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)H * n; i += (long)gridDim.x * blockDim.x) {
 		const int y = (int)(i / n), t = (int)(i % n);
-		volL[d * HW + (long)y * ld + t] = q;
-		volR[d * HW + (long)y * ld + (W - 1 - t)] = q;
+		if (volL) volL[d * HW + (long)y * ld + t] = q;
+		if (volR) volR[d * HW + (long)y * ld + (W - 1 - t)] = q;
 	}
 }
 
@@ -580,7 +525,7 @@ int adc_subpixel(const float *d0, const float *c2, float *out, int H, int W, int
 
 int adc_fill_invalid(float *volL, float *volR, int D, int H, int W, int ld, cudaStream_t s)
 {
-	if (!volL || !volR || D < 1 || H < 1 || W < 1 || ld < W) return ADCENSUS_EINVAL;
+	if ((!volL && !volR) || D < 1 || H < 1 || W < 1 || ld < W) return ADCENSUS_EINVAL;   // one of the two may be NULL (skipped)
 	if (D == 1) return 0;
 	dim3 grid(8, D - 1);
 	fill_invalid_kernel<<<grid, 256, 0, s>>>(volL, volR, D, H, W, ld);
@@ -681,22 +626,6 @@ int adcensus_Normalize_forward(const float *input, float *norm, float *output, i
 	return 0;
 }
 
-int adcensus_ad(const float *x0, const float *x1, float *out, int D, int H, int W, int direction, adcensus_stream_t stream)
-{
-	if (!x0 || !x1 || !out || D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1)) return ADCENSUS_EINVAL;
-	long size = (long)D * H * W;
-	LAUNCH1D(ad_kernel, size, adc_stream(stream), x0, x1, out, size, H, W, direction);
-	return 0;
-}
-
-int adcensus_census(const float *x0, const float *x1, float *out, int D, int nch, int H, int W, int direction, adcensus_stream_t stream)
-{
-	if (!x0 || !x1 || !out || D < 1 || nch < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1)) return ADCENSUS_EINVAL;
-	long size = (long)D * H * W;
-	LAUNCH1D(census_kernel, size, adc_stream(stream), x0, x1, out, size, nch, H, W, direction);
-	return 0;
-}
-
 int mccnn_fill_nan(float *p, size_t n, adcensus_stream_t stream)
 {
 	if (!p) return ADCENSUS_EINVAL;
@@ -724,6 +653,7 @@ int mccnn_fill_nan(float *p, size_t n, adcensus_stream_t stream)
 
 int mccnn_fill_invalid(float *volL, float *volR, int D, int H, int W, adcensus_stream_t stream)
 {
+	if (!volL || !volR) return ADCENSUS_EINVAL;
 	return adc_fill_invalid(volL, volR, D, H, W, W, adc_stream(stream));
 }
 
@@ -742,6 +672,24 @@ int mccnn_transpose_hwd_to_dhw_div4(const float *in, float *out, int D, int H, i
 {
 	if (!in || !out || in == out || D < 1 || H < 1 || W < 1) return ADCENSUS_EINVAL;
 	return adc_transpose(in, out, (long)H * W, D, 4.0f, true, adc_stream(stream));  // exact: x / 4
+}
+
+/* pitched (D, H, ld) forms of the Lua-side tensor ops, as the fused pipeline runs them */
+int mccnn_transpose_dhw_pitched_to_hwd(const float *in, float *out, int D, int H, int W, int ld, adcensus_stream_t stream)
+{
+	if (!in || !out || in == out || D < 1 || H < 1 || W < 1 || ld < W) return ADCENSUS_EINVAL;
+	return adc_transpose_dhw_pitched_to_hwd(in, out, D, H, W, ld, adc_stream(stream));
+}
+
+int mccnn_transpose_hwd_to_dhw_pitched_div4(const float *in, float *out, int D, int H, int W, int ld, adcensus_stream_t stream)
+{
+	if (!in || !out || in == out || D < 1 || H < 1 || W < 1 || ld < W) return ADCENSUS_EINVAL;
+	return adc_transpose_hwd_to_dhw_pitched_div4(in, out, D, H, W, ld, adc_stream(stream));
+}
+
+int mccnn_argmin_pitched(const float *vol, float *disp, int D, int H, int W, int ld, adcensus_stream_t stream)
+{
+	return adc_argmin_pitched(vol, disp, D, H, W, ld, adc_stream(stream));
 }
 
 int mccnn_gaussian(double sigma, float *out_host)

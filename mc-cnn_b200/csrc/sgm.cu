@@ -45,6 +45,12 @@ struct SgmParams {
 	// image; its pixel (y, x) is image pixel (yoff + y, xoff + x) of the Ht x Wt image the class
 	// tables were built from.  Bands never cut a scanline of the pass they are used for.
 	int Ht, Wt, yoff, xoff;
+	// vertical scans over a ROW band of the image (wavefront split, rowband.py): the line state L_r(p - r, .) of the
+	// row before the band enters through state_in and leaves through state_out ([line][32*K] floats; NULL: the scan
+	// starts / ends at the image border); line0 .. line1: the scanlines (columns) of this launch
+	const float *state_in;
+	float *state_out;
+	int line0, line1;
 };
 
 // ---------------------------------------------------------------- penalty class tables
@@ -332,7 +338,8 @@ struct SgmScan {
 	// steps [s_begin, s_end) of the scan; use_out: read-modify-write the accumulator (else it is
 	// known to hold zeros).  Streams the cost (and accumulator) vectors of the next PF pixels into
 	// the shared-memory ring with cp.async; every lane fetches exactly the elements it consumes.
-	__device__ __forceinline__ void run(int s_begin, int s_end, bool use_out)
+	// carried: the scan continues a line whose state is already in `prev` (vertical wavefront): step 0 is an ordinary step
+	__device__ __forceinline__ void run(int s_begin, int s_end, bool use_out, bool carried = false)
 	{
 #pragma unroll
 		for (int u = 0; u < PF; u++) {
@@ -340,7 +347,7 @@ struct SgmScan {
 				issue_vec<K, VEC>(ring + (u * 2) * VSZ, in + base + u * pix_step, dbase, D);
 				if (use_out) issue_vec<K, VEC>(ring + (u * 2 + 1) * VSZ, out + base + u * pix_step, dbase, D);
 				if constexpr (!HORIZ)
-					if (s_begin + u >= 1) cls_issue(u, u);
+					if (s_begin + u >= 1 || carried) cls_issue(u, u);
 			}
 			asm volatile("cp.async.commit_group;");
 		}
@@ -356,7 +363,7 @@ struct SgmScan {
 			if (use_out) read_slot<K>(cout, rs + VSZ);
 
 			float val[K];
-			if (s == 0) {                                   // adcensus.cu:567-572
+			if (s == 0 && !carried) {                       // adcensus.cu:567-572
 #pragma unroll
 				for (int k = 0; k < K; k++) val[k] = cin[k];
 			} else {
@@ -433,8 +440,8 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 	using Scan = SgmScan<K, VEC, SD, PF>;
 	const int wib = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
-	const int line = blockIdx.x * WPB + wib;
-	if (line >= (SD < 2 ? H : W)) return;          // whole warp
+	const int line = prm.line0 + blockIdx.x * WPB + wib;
+	if (line >= prm.line1) return;                 // whole warp
 	float *ring = sgm_smem + (size_t)wib * PF * 2 * Scan::VSZ;
 	unsigned *extra = reinterpret_cast<unsigned *>(sgm_smem + (size_t)WPB * PF * 2 * Scan::VSZ);
 	const uint8_t *s1 = nullptr, *s2 = nullptr;
@@ -452,7 +459,21 @@ sgm_pass_kernel(const uint8_t *__restrict__ tab, const float *__restrict__ in, f
 	}
 	Scan sc;
 	sc.init(tab, in, out, ring + lane * K, cring, s1, s2, H, W, D, pad, prm, line);
-	sc.run(0, SD < 2 ? W : H, !ZERO);
+	bool carried = false;
+	if constexpr (SD >= 2) {
+		if (prm.state_in) {                            // line state of the row before this band
+			carried = true;
+#pragma unroll
+			for (int k = 0; k < K; k++) sc.prev[k] = prm.state_in[(long)line * Scan::VSZ + lane * K + k];
+		}
+	}
+	sc.run(0, SD < 2 ? W : H, !ZERO, carried);
+	if constexpr (SD >= 2) {
+		if (prm.state_out) {
+#pragma unroll
+			for (int k = 0; k < K; k++) prm.state_out[(long)line * Scan::VSZ + lane * K + k] = sc.prev[k];
+		}
+	}
 }
 
 // Both horizontal directions of one image row in ONE CTA (two warps), for an accumulator that is
@@ -525,7 +546,8 @@ int launch_pass(const uint8_t *tab, const float *in, float *out, int H, int W, i
 	static bool done[64] = {false};
 	int rc = sgm_allow_smem(kern, smem, done);
 	if (rc) return rc;
-	const int nlines = SD < 2 ? H : W;
+	const int nlines = prm.line1 - prm.line0;
+	if (nlines <= 0) return 0;
 	kern<<<adc_div_up(nlines, WPB), 32 * WPB, smem, s>>>(tab, in, out, H, W, D, pad, prm);
 	ADC_CHECK_LAUNCH();
 	return 0;
@@ -552,18 +574,21 @@ int launch_all(const uint8_t *tab, const float *in, float *out, int H, int W, in
 	       const SgmParams &prm, bool zero_out, int pass_mask, cudaStream_t s)
 {
 	int rc = 0;
+	SgmParams ph = prm, pv = prm;                     // horizontal scans: every row; vertical: the caller's column range (default all)
+	ph.line0 = 0; ph.line1 = H; ph.state_in = nullptr; ph.state_out = nullptr;
+	if (pv.line1 <= pv.line0) { pv.line0 = 0; pv.line1 = W; }
 	if ((pass_mask & 3) == 3 && zero_out && W >= 2) {
-		rc = launch_hpair<K, VEC>(tab, in, out, H, W, D, pad, prm, s);   // right and left concurrently
+		rc = launch_hpair<K, VEC>(tab, in, out, H, W, D, pad, ph, s);   // right and left concurrently
 	} else {
 		if (pass_mask & 1)
-			rc = zero_out ? launch_pass<K, VEC, 0, true>(tab, in, out, H, W, D, pad, prm, s)
-				      : launch_pass<K, VEC, 0, false>(tab, in, out, H, W, D, pad, prm, s);
+			rc = zero_out ? launch_pass<K, VEC, 0, true>(tab, in, out, H, W, D, pad, ph, s)
+				      : launch_pass<K, VEC, 0, false>(tab, in, out, H, W, D, pad, ph, s);
 		if (rc) return rc;
-		if ((pass_mask & 2) && (rc = launch_pass<K, VEC, 1, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
+		if ((pass_mask & 2) && (rc = launch_pass<K, VEC, 1, false>(tab, in, out, H, W, D, pad, ph, s))) return rc;
 	}
 	if (rc) return rc;
-	if ((pass_mask & 4) && (rc = launch_pass<K, VEC, 2, false>(tab, in, out, H, W, D, pad, prm, s))) return rc;
-	if (pass_mask & 8) rc = launch_pass<K, VEC, 3, false>(tab, in, out, H, W, D, pad, prm, s);
+	if ((pass_mask & 4) && (rc = launch_pass<K, VEC, 2, false>(tab, in, out, H, W, D, pad, pv, s))) return rc;
+	if (pass_mask & 8) rc = launch_pass<K, VEC, 3, false>(tab, in, out, H, W, D, pad, pv, s);
 	return rc;
 }
 
@@ -588,25 +613,32 @@ int adc_sgm_classes(const float *x0, const float *x1, uint8_t *tab, int Ht, int 
 // The selected passes over a volume (H,W,D) that is the band [yoff, yoff+H) x [xoff, xoff+W) of the
 // Ht x Wt image whose class tables are in `tab` (adc_sgm_classes).  zero_out: `output` is known
 // to be all zeros (main.lua:1014) -> the first (rightward) pass skips reading it.
-int adc_sgm2_band(const float *in, float *out, const uint8_t *tab, int H, int W, int D, int Ht, int Wt, int yoff, int xoff,
-		  float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
-		  bool zero_out, int pass_mask, cudaStream_t s)
+// selector words of the vertical scans for the W columns at image offset xoff (all Ht table rows) and one `direction`
+int adc_sgm_selectors(uint8_t *tab, int W, int D, int Ht, int Wt, int xoff, int direction, cudaStream_t s)
 {
-	SgmParams prm{pi1, pi2, tau_so, alpha1, q1, q2, direction, Ht, Wt, yoff, xoff};
 	const int pad = sgm_slots(D);
-	if (pass_mask & 12) {                              // vertical scans: band = whole columns (H == Ht)
-		unsigned *sel = reinterpret_cast<unsigned *>(const_cast<uint8_t *>(tab) + sgm_sel_offset(Ht, Wt + 2 * pad));
-		if (Ht > 65535) return ADCENSUS_ELIMIT;            // gridDim.y
-		const dim3 grid(adc_div_up(W, 8), Ht), block(32, 8);
-		switch (pad / 32) {
-		case 1: sgm_sel_kernel<1><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
-		case 2: sgm_sel_kernel<2><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
-		case 4: sgm_sel_kernel<4><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
-		case 8: sgm_sel_kernel<8><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
-		default: sgm_sel_kernel<16><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
-		}
-		ADC_CHECK_LAUNCH();
+	unsigned *sel = reinterpret_cast<unsigned *>(tab + sgm_sel_offset(Ht, Wt + 2 * pad));
+	if (Ht > 65535) return ADCENSUS_ELIMIT;            // gridDim.y
+	const dim3 grid(adc_div_up(W, 8), Ht), block(32, 8);
+	switch (pad / 32) {
+	case 1: sgm_sel_kernel<1><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
+	case 2: sgm_sel_kernel<2><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
+	case 4: sgm_sel_kernel<4><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
+	case 8: sgm_sel_kernel<8><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
+	default: sgm_sel_kernel<16><<<grid, block, 0, s>>>(tab, sel, Ht, W, Wt + 2 * pad, pad, xoff, direction); break;
 	}
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+// the selected passes with tables (and, for vertical passes, selectors) already built; vertical passes may cover the
+// columns [xa, xb) only and carry the line state across row bands (state_in / state_out, [W][32K] floats, NULL = border)
+int adc_sgm2_passes(const float *in, float *out, const uint8_t *tab, int H, int W, int D, int Ht, int Wt, int yoff, int xoff,
+		    float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
+		    bool zero_out, int pass_mask, int xa, int xb, const float *state_in, float *state_out, cudaStream_t s)
+{
+	SgmParams prm{pi1, pi2, tau_so, alpha1, q1, q2, direction, Ht, Wt, yoff, xoff, state_in, state_out, xa, xb};
+	const int pad = sgm_slots(D);
 	const bool vec = (D % 4 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0);
 	if (D <= 32) return launch_all<1, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
 	if (D <= 64) return launch_all<2, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
@@ -617,6 +649,19 @@ int adc_sgm2_band(const float *in, float *out, const uint8_t *tab, int H, int W,
 	return vec ? launch_all<16, true>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s)
 		   : launch_all<16, false>(tab, in, out, H, W, D, pad, prm, zero_out, pass_mask, s);
 }
+
+int adc_sgm2_band(const float *in, float *out, const uint8_t *tab, int H, int W, int D, int Ht, int Wt, int yoff, int xoff,
+		  float pi1, float pi2, float tau_so, float alpha1, float q1, float q2, int direction,
+		  bool zero_out, int pass_mask, cudaStream_t s)
+{
+	if (pass_mask & 12) {                              // vertical scans: band = whole columns (H == Ht)
+		int rc = adc_sgm_selectors(const_cast<uint8_t *>(tab), W, D, Ht, Wt, xoff, direction, s);
+		if (rc) return rc;
+	}
+	return adc_sgm2_passes(in, out, tab, H, W, D, Ht, Wt, yoff, xoff, pi1, pi2, tau_so, alpha1, q1, q2, direction, zero_out, pass_mask,
+			       0, 0, nullptr, nullptr, s);
+}
+
 
 // whole image, all four directions (what adcensus.sgm2 does).  tab: scratch of adc_sgm_table_bytes(H, W, D) bytes.
 int adc_sgm2(const float *x0, const float *x1, const float *in, float *out, uint8_t *tab, int H, int W, int D,
@@ -670,4 +715,40 @@ extern "C" int adcensus_sgm2(const float *x0, const float *x1, const float *inpu
 	rc = adc_sgm2(x0, x1, input, output, tab, H, W, D, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction, false, s);
 	int rc2 = adc_scratch_free(tab, s);
 	return rc ? rc : rc2;
+}
+
+// ---- wavefront split of the vertical scans over ROW bands (rowband.py) ------------------------------------------
+// The class tables of an image pair are built once (mccnn_sgm_tables_build: classes + the selector words of one
+// `direction`), then the passes run band by band: horizontal passes are band-local; a vertical pass over the rows
+// [yoff, yoff + H) of the columns [xa, xb) takes the line state of the row before the band from state_in (NULL: the band
+// touches the image border where the scan starts) and leaves the state of its last row in state_out ([W][sgm_state_pitch]
+// floats), so that consecutive bands -- on different GPUs -- chain column chunk by column chunk.
+extern "C" size_t mccnn_sgm_tables_bytes(int Ht, int Wt, int D) { return adc_sgm_table_bytes(Ht, Wt, D); }
+extern "C" int mccnn_sgm_state_pitch(int D) { return sgm_slots(D); }
+
+extern "C" int mccnn_sgm_tables_build(const float *x0, const float *x1, void *tab, int Ht, int Wt, int D, float tau_so,
+				      int direction, adcensus_stream_t stream)
+{
+	if (!x0 || !x1 || !tab || Ht < 1 || Wt < 1 || D < 1 || (direction != 1 && direction != -1)) return ADCENSUS_EINVAL;
+	if (D > ADCENSUS_MAX_DISP) return ADCENSUS_ELIMIT;
+	int rc = adc_sgm_classes(x0, x1, (uint8_t *)tab, Ht, Wt, D, tau_so, adc_stream(stream));
+	if (!rc) rc = adc_sgm_selectors((uint8_t *)tab, Wt, D, Ht, Wt, 0, direction, adc_stream(stream));
+	return rc;
+}
+
+extern "C" int mccnn_sgm2_rows(const void *tab, const float *input, float *output, int H, int W, int D, int Ht, int yoff,
+			       float pi1, float pi2, float tau_so, float alpha1, float sgm_q1, float sgm_q2,
+			       int direction, int pass_mask, int zero_out, int xa, int xb,
+			       const float *state_in, float *state_out, adcensus_stream_t stream)
+{
+	if (!tab || !input || !output || input == output) return ADCENSUS_EINVAL;
+	if (H < 1 || W < 1 || D < 1 || Ht < H || yoff < 0 || yoff + H > Ht) return ADCENSUS_EINVAL;
+	if ((direction != 1 && direction != -1) || (pass_mask & ~15) || !pass_mask) return ADCENSUS_EINVAL;
+	if ((pass_mask & 12) && (xa < 0 || xb > W || xa >= xb)) return ADCENSUS_EINVAL;
+	if ((pass_mask & 12) == 12 && (state_in || state_out)) return ADCENSUS_EINVAL;   // one vertical direction per call when chained
+	if ((pass_mask & 4) && !state_in && yoff != 0) return ADCENSUS_EINVAL;           // a band below the top needs the state above it
+	if ((pass_mask & 8) && !state_in && yoff + H != Ht) return ADCENSUS_EINVAL;
+	if (D > ADCENSUS_MAX_DISP) return ADCENSUS_ELIMIT;
+	return adc_sgm2_passes(input, output, (const uint8_t *)tab, H, W, D, Ht, W, yoff, 0, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2,
+			       direction, zero_out != 0, pass_mask, xa, xb, state_in, state_out, adc_stream(stream));
 }

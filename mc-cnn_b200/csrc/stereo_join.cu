@@ -216,6 +216,7 @@ stereo_join_kernel(const __grid_constant__ CUtensorMap tmL, const float *__restr
 			}
 		}
 	}
+	if (FASTIO) fence_proxy_async_smem();                // generic-proxy writes of `so` before the async-proxy (TMA) read
 	__syncthreads();
 
 	const int nrows = min(DC, D - d0);
@@ -227,10 +228,10 @@ stereo_join_kernel(const __grid_constant__ CUtensorMap tmL, const float *__restr
 				const int r = idx >> 7, x = X0 + (idx & (SJ_TX - 1));
 				if (x < d0 + r || x >= W) so[idx] = q;
 			}
+			fence_proxy_async_smem();
 			__syncthreads();
 		}
 		if (tid == 0) {
-			fence_proxy_async_smem();
 			tma_store_3d(&tmL, so, X0, y, d0);           // outL[d0 .. d0+DC) x row y x [X0, X0+128): clipped at D and W (adcensus.cu:1472)
 			tma_store_commit();
 		}
@@ -322,8 +323,8 @@ int sj_ns(int D)
 
 // outputs (D, H, ldo) with row pitch ldo >= W (the fused pipeline's private volumes); features (C, H, W) contiguous.
 // The fast load / store path needs W even, 8-byte aligned features and 16-byte aligned outputs with ldo % 4 == 0; it
-// writes NaN into the left volume's entries x < d (no separate fill needed there) and leaves the right volume's
-// invalid entries untouched, like the reference.  tmL: tensor map of output_L with box {128, 1, adc_stereo_join_dc(D)}
+// writes NaN into the left volume's entries x < d (no separate fill needed there; hence opt-in through `fast`: the
+// operator itself leaves them untouched, adcensus.cu:1467) and leaves the right volume's invalid entries untouched.  tmL: tensor map of output_L with box {128, 1, adc_stereo_join_dc(D)}
 // (NULL: encoded here).
 int adc_stereo_join_dc(int D) { return 16 * sj_ns(D) - 8; }
 
@@ -334,13 +335,13 @@ int adc_stereo_join_fast_ok(const float *input_L, const float *input_R, const fl
 }
 
 int adc_stereo_join(const float *input_L, const float *input_R, float *output_L, float *output_R,
-		    int C, int D, int H, int W, int ldo, const CUtensorMap *tmL, cudaStream_t s)
+		    int C, int D, int H, int W, int ldo, int fast, const CUtensorMap *tmL, cudaStream_t s)
 {
 	if (!input_L || !input_R || !output_L || !output_R) return ADCENSUS_EINVAL;
 	if (C < 1 || D < 1 || H < 1 || W < 1 || H > 65535 || ldo < W) return ADCENSUS_EINVAL;
 	if (C > 128) return ADCENSUS_ELIMIT;  // reference: float L_cache[128] (adcensus.cu:1460-1461)
 	const int ns = sj_ns(D);
-	if (ldo > W && adc_stereo_join_fast_ok(input_L, input_R, output_L, output_R, W, ldo)) {
+	if (fast && adc_stereo_join_fast_ok(input_L, input_R, output_L, output_R, W, ldo)) {
 		CUtensorMap local;
 		if (!tmL) {
 			const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)D};
@@ -360,5 +361,16 @@ int adc_stereo_join(const float *input_L, const float *input_R, float *output_L,
 extern "C" int adcensus_StereoJoin(const float *input_L, const float *input_R, float *output_L, float *output_R,
 				   int C, int D, int H, int W, adcensus_stream_t stream)
 {
-	return adc_stereo_join(input_L, input_R, output_L, output_R, C, D, H, W, W, nullptr, adc_stream(stream));
+	return adc_stereo_join(input_L, input_R, output_L, output_R, C, D, H, W, W, /*fast=*/0, nullptr, adc_stream(stream));
+}
+
+// StereoJoin into pitched (D, H, ld) volumes (the fused pipeline's private layout).  Unlike the operator above this
+// form also performs the fill of main.lua:946 for the LEFT volume (entries x < d become NaN); the right volume's
+// invalid entries (x >= W - d) are left untouched, the caller fills them (mccnn_fill_invalid / adc_fill_invalid).
+extern "C" int mccnn_stereo_join_pitched(const float *input_L, const float *input_R, float *output_L, float *output_R,
+					 int C, int D, int H, int W, int ld, adcensus_stream_t stream)
+{
+	if (!input_L || !input_R || !output_L || !output_R || ld < W) return ADCENSUS_EINVAL;
+	if (!adc_stereo_join_fast_ok(input_L, input_R, output_L, output_R, W, ld)) return ADCENSUS_EINVAL;
+	return adc_stereo_join(input_L, input_R, output_L, output_R, C, D, H, W, ld, /*fast=*/1, nullptr, adc_stream(stream));
 }

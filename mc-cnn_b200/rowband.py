@@ -6,14 +6,18 @@ from BASELINE.json's wording:
 
 * StereoJoin, fix_border, the permutes, argmin, sub-pixel: row-local -> no communication;
 * cross: needs image rows +- L1 -> both (small) images are replicated on every rank;
-* cbca: the vertical arm reaches (max(L1,2)-1) rows into the neighbouring bands -> a halo of that
-  many volume rows is exchanged with the two neighbours before EVERY iteration (send/recv);
-* sgm2: the two horizontal passes are band-local; the two vertical passes are a serial chain over
-  the rows, so the accumulator and the cost volume are RE-PARTITIONED into column bands (one
-  all-to-all each, every rank sends (N-1)/N of its band), the vertical passes run on whole
-  columns, and the accumulator comes back (one more all-to-all).  Direction order and therefore
-  the accumulation order (right, left, down, up) are the reference's => results are bit-identical
-  to the single-GPU pipeline (tests/test_rowband_*.py);
+* cbca: the vertical arm reaches halo = max(L1,2)-1 rows into the neighbouring bands PER ITERATION.  A block of n
+  iterations is run on the band extended by n * halo rows on either side (the valid part shrinks by `halo` rows per
+  iteration and ends on the band): for the first block (cbca_i1) the extension costs nothing but arithmetic -- the
+  features are replicated, StereoJoin simply covers the extended rows -- and the second block (cbca_i2, after SGM)
+  needs ONE halo exchange with the two neighbours instead of one per iteration (falls back to one exchange per
+  iteration when n * halo rows exceed a neighbour's band);
+* sgm2: the two horizontal passes are band-local.  The two vertical passes are serial chains over the rows: they run as a
+  WAVEFRONT over column chunks -- rank r scans its rows of chunk k as soon as rank r-1 (down pass; r+1 for the up pass)
+  has sent the line state of its last row for that chunk (W/K x D floats), and passes its own last row's state on.
+  Only that boundary state crosses a band (SURVEY.md 8e design A), not the volumes; the pipeline fill costs (N-1)/K of
+  a pass.  Direction order and therefore the accumulation order (right, left, down, up) are the reference's =>
+  results are bit-identical to the single-GPU pipeline in its exact mode (tests/test_rowband_*.py);
 * LR check / interpolations / median / bilateral work on H x W maps: the disparity maps are
   all-gathered (tiny) and these stages run replicated; sub-pixel refinement reads the band's own
   left volume.
@@ -64,43 +68,14 @@ class Comm:
         self.exchange(sends, recvs)
         return full
 
-    def rows_to_cols(self, t, H, W):
-        """(Hb, W, D) row band -> (H, Wb, D) column band (all-to-all)"""
-        if not self.on:
-            return t
-        D = t.shape[2]
-        x0, x1 = split(W, self.world, self.rank)
-        out = t.new_empty((H, x1 - x0, D))
-        sends, recvs = {}, {}
-        for p in range(self.world):
-            a, b = split(W, self.world, p)
-            sends[p] = t[:, a:b, :]
-            ya, yb = split(H, self.world, p)
-            recvs[p] = out[ya:yb]                      # contiguous: rows are the outermost axis
-        y0, y1 = split(H, self.world, self.rank)
-        out[y0:y1] = t[:, x0:x1, :]
-        self.exchange(sends, recvs)
-        return out
+    def send(self, t, peer):
+        """stream-ordered (nccl) / blocking (gloo) point-to-point send of a contiguous tensor"""
+        if self.on:
+            dist.send(t, peer)
 
-    def cols_to_rows(self, t, H, W):
-        """(H, Wb, D) column band -> (Hb, W, D) row band (all-to-all back)"""
-        if not self.on:
-            return t
-        D = t.shape[2]
-        y0, y1 = split(H, self.world, self.rank)
-        out = t.new_empty((y1 - y0, W, D))
-        sends, recvs, stage = {}, {}, {}
-        for p in range(self.world):
-            ya, yb = split(H, self.world, p)
-            sends[p] = t[ya:yb]
-            a, b = split(W, self.world, p)
-            stage[p] = t.new_empty((y1 - y0, b - a, D))  # strided destination: receive, then place
-            recvs[p] = stage[p]
-        self.exchange(sends, recvs)
-        for p in range(self.world):
-            a, b = split(W, self.world, p)
-            out[:, a:b, :] = t[y0:y1] if p == self.rank else stage[p]
-        return out
+    def recv(self, t, peer):
+        if self.on:
+            dist.recv(t, peer)
 
     def halo(self, vol, n):
         """vol (D, Hb, W): returns (rows from the band above, rows from the band below), each
@@ -122,11 +97,12 @@ class Comm:
         return top, bot
 
 
-def stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm=None):
+def stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm=None, chunks=None):
     """main.lua:929-1082 (arch 'fast') with the rows of one pair split over the ranks of `comm`.
 
     featL/featR (C,H,W) and imgL/imgR (H,W) are the FULL tensors on every rank (only this rank's
-    rows of the features are read).  Returns the full (H,W) disparity map on every rank.
+    rows of the features are read).  `chunks`: column chunks of the vertical SGM wavefront (default: 4 per rank, at
+    least 32 columns each).  Returns the full (H,W) disparity map on every rank.
     """
     comm = comm or Comm()
     H, W = imgL.shape
@@ -135,49 +111,83 @@ def stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm=None):
     Hb = y1 - y0
     max_arm = max(int(opt.L1), 2)
     halo = max_arm - 1 if (opt.cbca_i1 + opt.cbca_i2) > 0 else 0
+    band_min = min(split(H, N, p)[1] - split(H, N, p)[0] for p in range(N))
     if N > 1:
-        assert min(split(H, N, p)[1] - split(H, N, p)[0] for p in range(N)) >= max(halo, 1), "bands thinner than the CBCA halo"
+        assert band_min >= max(halo, 1), "bands thinner than the CBCA halo"
         assert max_arm <= 14, "row-band CBCA supports arms up to 14 pixels"
+    K = chunks if chunks else max(1, min(4 * N, W // 32)) if N > 1 else 1
 
-    volL, volR = ops.stereo_join(featL[:, y0:y1].contiguous(), featR[:, y0:y1].contiguous(), D)     # :946-947
+    # first CBCA block on the band extended by cbca_i1 * halo rows: StereoJoin covers the extension (features are replicated)
+    e1 = halo * int(opt.cbca_i1)
+    ya, yb = max(0, y0 - e1), min(H, y1 + e1)
+    volL, volR = ops.stereo_join(featL[:, ya:yb].contiguous(), featR[:, ya:yb].contiguous(), D)     # :946-947
     ops.fix_border(volL, opt.border, -1)                                                             # :948
     ops.fix_border(volR, opt.border, 1)                                                              # :949
     x0c = ops.cross(imgL, opt.L1, opt.tau1)                                                          # :995 (full image)
     x1c = ops.cross(imgR, opt.L1, opt.tau1)                                                          # :996
 
-    def band_arms(arms, ya, yb):
-        """arms of rows [ya, yb) in the coordinates of that sub-image; vertical end-points clamped to it
-        (only halo rows are affected, whose outputs are discarded)"""
-        a = arms[:, ya:yb].clone()
-        a[2] = torch.clamp(a[2] - ya, min=-1)
-        a[3] = torch.clamp(a[3] - ya, max=yb - ya)
-        return a.contiguous()
+    def band_arms(arms, a, b):
+        """arms of rows [a, b) in the coordinates of that sub-image; vertical end-points clamped to it
+        (only rows whose outputs are discarded are affected)"""
+        q = arms[:, a:b].clone()
+        q[2] = torch.clamp(q[2] - a, min=-1)
+        q[3] = torch.clamp(q[3] - a, max=b - a)
+        return q.contiguous()
 
-    def cbca_band(vol, direction):
-        top, bot = comm.halo(vol, halo)
-        ext = torch.cat([top, vol, bot], dim=1).contiguous() if (top.shape[1] or bot.shape[1]) else vol
-        ya, yb = y0 - top.shape[1], y1 + bot.shape[1]
-        out = ops.cbca(band_arms(x0c, ya, yb), band_arms(x1c, ya, yb), ext, direction, max_arm)
-        return out[:, top.shape[1]: top.shape[1] + Hb].contiguous()
+    def cbca_block(ext, a, b, n, direction):
+        """n iterations on the extended band rows [a, b) (which hold valid data for all of [a, b)); rows closer than
+        n * halo to an artificial edge end up invalid and are cut off by the caller"""
+        if n == 0:
+            return ext
+        a0, a1 = band_arms(x0c, a, b), band_arms(x1c, a, b)
+        for _ in range(n):
+            ext = ops.cbca(a0, a1, ext, direction, max_arm)
+        return ext
+
+    def cbca_exchanging(vol, n, direction):
+        """n iterations on the band [y0, y1): one exchange of n * halo rows when the neighbours hold that many, else one
+        exchange of `halo` rows per iteration"""
+        if n == 0 or halo == 0 or N == 1:
+            return cbca_block(vol, y0, y1, n, direction)
+        steps = [n] if n * halo <= band_min else [1] * n
+        for m in steps:
+            top, bot = comm.halo(vol, m * halo)
+            ext = torch.cat([top, vol, bot], dim=1).contiguous() if (top.shape[1] or bot.shape[1]) else vol
+            out = cbca_block(ext, y0 - top.shape[1], y1 + bot.shape[1], m, direction)
+            vol = out[:, top.shape[1]: top.shape[1] + Hb].contiguous()
+        return vol
+
+    def vertical_wavefront(tab, cost, acc, direction, sd):
+        """one vertical pass (sd 2 down, 3 up) chained over the ranks, column chunk by column chunk"""
+        prev, nxt = (r + 1, r - 1) if sd == 3 else (r - 1, r + 1)      # in scan order
+        has_prev, has_next = 0 <= prev < N, 0 <= nxt < N
+        st_in = ops.new_state(W, D, cost) if has_prev else None
+        st_out = ops.new_state(W, D, cost) if has_next else None
+        for k in range(K):
+            xa, xb = split(W, K, k)
+            if xa == xb:
+                continue
+            if has_prev:
+                comm.recv(st_in[xa:xb], prev)
+            ops.sgm_rows(tab, cost, acc, H, y0, opt, direction, 1 << sd, False, xa, xb, st_in, st_out)
+            if has_next:
+                comm.send(st_out[xa:xb], nxt)
 
     disp = {}
     vol_left = None
-    x0b, x1b = split(W, N, r)
     for direction in (1, -1):                                                                        # :955
-        vol = volL if direction == -1 else volR                                                      # :986
-        for _ in range(opt.cbca_i1):                                                                 # :998-1001
-            vol = cbca_band(vol, direction)
+        ext = volL if direction == -1 else volR                                                      # :986
+        ext = cbca_block(ext, ya, yb, int(opt.cbca_i1), direction)                                   # :998-1001
+        vol = ext[:, y0 - ya: y0 - ya + Hb].contiguous() if (ya != y0 or yb != y1) else ext
         for _ in range(opt.sgm_i):                                                                   # :1008-1020
+            tab = ops.sgm_tables(imgL, imgR, D, opt, direction)
             cost = ops.to_hwd(vol)                                                                   # (Hb, W, D)
             acc = ops.zeros_like(cost)                                                               # :1014
-            ops.sgm_band(imgL, imgR, cost, acc, H, W, y0, 0, opt, direction, 3, True)                # right, left
-            cost_c = comm.rows_to_cols(cost, H, W)
-            acc_c = comm.rows_to_cols(acc, H, W)
-            ops.sgm_band(imgL, imgR, cost_c, acc_c, H, W, 0, x0b, opt, direction, 12, False)         # down, up
-            acc = comm.cols_to_rows(acc_c, H, W)
+            ops.sgm_rows(tab, cost, acc, H, y0, opt, direction, 3, True, 0, W, None, None)           # right, left: band-local
+            vertical_wavefront(tab, cost, acc, direction, 2)                                         # down
+            vertical_wavefront(tab, cost, acc, direction, 3)                                         # up
             vol = ops.from_hwd_div4(acc)                                                             # :1017-1020
-        for _ in range(opt.cbca_i2):                                                                 # :1035-1038
-            vol = cbca_band(vol, direction)
+        vol = cbca_exchanging(vol, int(opt.cbca_i2), direction)                                      # :1035-1038
         disp[direction] = comm.all_gather_rows(ops.argmin(vol), H)                                   # :1049-1050
         if direction == -1:
             vol_left = vol
@@ -254,6 +264,43 @@ class CudaOps:
                                                 f(opt.sgm_q2), int(direction), int(pass_mask), int(bool(zero_out)),
                                                 adcensus._stream(cost))
         adcensus._check(rc, "mccnn_sgm2_band")
+
+    def sgm_tables(self, imgL, imgR, D, opt, direction):
+        """penalty-class tables + selector words of the full image pair for one `direction` (mccnn_sgm_tables_build)"""
+        import ctypes
+
+        from . import adcensus
+
+        lib = adcensus.lib()
+        lib.mccnn_sgm_tables_bytes.restype = ctypes.c_size_t
+        Ht, Wt = imgL.shape
+        tab = torch.empty(lib.mccnn_sgm_tables_bytes(Ht, Wt, D), dtype=torch.uint8, device=imgL.device)
+        p = lambda t: adcensus._t(t, 0, "mccnn_sgm_tables_build")
+        with torch.cuda.device(imgL.device):
+            rc = lib.mccnn_sgm_tables_build(p(imgL.contiguous()), p(imgR.contiguous()), ctypes.c_void_p(tab.data_ptr()), Ht, Wt, D,
+                                            ctypes.c_float(opt.tau_so), int(direction), adcensus._stream(imgL))
+        adcensus._check(rc, "mccnn_sgm_tables_build")
+        return tab
+
+    def new_state(self, W, D, like):
+        from . import adcensus
+
+        return torch.empty((W, adcensus.lib().mccnn_sgm_state_pitch(D)), device=like.device, dtype=torch.float32)
+
+    def sgm_rows(self, tab, cost, acc, Ht, yoff, opt, direction, pass_mask, zero_out, xa, xb, state_in, state_out):
+        import ctypes
+
+        from . import adcensus
+
+        H, W, D = cost.shape
+        f = ctypes.c_float
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+        with torch.cuda.device(cost.device):
+            rc = adcensus.lib().mccnn_sgm2_rows(p(tab), p(cost), p(acc), H, W, D, int(Ht), int(yoff), f(opt.pi1), f(opt.pi2),
+                                                f(opt.tau_so), f(opt.alpha1), f(opt.sgm_q1), f(opt.sgm_q2), int(direction),
+                                                int(pass_mask), int(bool(zero_out)), int(xa), int(xb), p(state_in), p(state_out),
+                                                adcensus._stream(cost))
+        adcensus._check(rc, "mccnn_sgm2_rows")
 
     def argmin(self, vol):
         from . import adcensus

@@ -212,10 +212,26 @@ void orc_cbca(const float *x0c, const float *x1c, const float *vol, float *out, 
  * size1=H, size2=W, size3=D).  tmp is indexed d*W + line (:570,576,617), so
  * the horizontal passes need H <= W.  out is accumulated into (+=).
  */
+/* image_rows > 0: the volume is a ROW band of an image with image_rows rows and the vertical scans continue across
+ * bands -- `tmp` carries the line state in and out, and "first pixel of the line" is decided in image coordinates */
+static void sgm2_step_ex(int sgm_direction, int line, int step,
+		      const float *x0, const float *x1, const float *in, float *out, float *tmp,
+		      int H, int W, int D, float pi1, float pi2, float tau_so, float alpha1,
+		      float sgm_q1, float sgm_q2, int direction, int Wt, int yoff, int xoff, int image_rows);
+
 static void sgm2_step(int sgm_direction, int line, int step,
 		      const float *x0, const float *x1, const float *in, float *out, float *tmp,
 		      int H, int W, int D, float pi1, float pi2, float tau_so, float alpha1,
 		      float sgm_q1, float sgm_q2, int direction, int Wt, int yoff, int xoff)
+{
+	sgm2_step_ex(sgm_direction, line, step, x0, x1, in, out, tmp, H, W, D, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction,
+		     Wt, yoff, xoff, 0);
+}
+
+static void sgm2_step_ex(int sgm_direction, int line, int step,
+		      const float *x0, const float *x1, const float *in, float *out, float *tmp,
+		      int H, int W, int D, float pi1, float pi2, float tau_so, float alpha1,
+		      float sgm_q1, float sgm_q2, int direction, int Wt, int yoff, int xoff, int image_rows)
 {
 	/* (H,W,D) may be a band of the Ht x Wt image: volume pixel (y,x) is image pixel (yoff+y, xoff+x);
 	 * a band holds whole scanlines of the passes run on it, so the first-pixel test stays in volume
@@ -227,7 +243,9 @@ static void sgm2_step(int sgm_direction, int line, int step,
 	else { x = line; y = H - 1 - step; dx = 0; dy = -1; }
 
 	long base = ((long)y * W + x) * D;
-	if (y - dy < 0 || y - dy >= H || x - dx < 0 || x - dx >= W) {       /* :567-572 */
+	int first = (y - dy < 0 || y - dy >= H || x - dx < 0 || x - dx >= W);   /* :567-572 */
+	if (image_rows > 0 && dy != 0) first = (y + yoff - dy < 0 || y + yoff - dy >= image_rows);
+	if (first) {
 		for (int d = 0; d < D; d++) {
 			float val = in[base + d];
 			out[base + d] += val;
@@ -282,6 +300,19 @@ void orc_sgm2_band(const float *x0, const float *x1, const float *in, float *out
 				sgm2_step(sd, line, step, x0, x1, in, out, tmp, H, W, D, pi1, pi2, tau_so,
 					  alpha1, sgm_q1, sgm_q2, direction, Wt, yoff, xoff);
 	}
+}
+
+/* one vertical pass (sd 2 down / 3 up) over the rows [yoff, yoff + H) of an image with Ht rows, columns [xa, xb); the line
+ * state enters and leaves through tmp (D x W, d * W + line): the CPU statement of mccnn_sgm2_rows' chained vertical scans */
+void orc_sgm2_vrows(const float *x0, const float *x1, const float *in, float *out, float *tmp,
+		    int H, int W, int D, int Ht, int yoff, float pi1, float pi2, float tau_so, float alpha1,
+		    float sgm_q1, float sgm_q2, int direction, int sd, int xa, int xb)
+{
+#pragma omp parallel for
+	for (int line = xa; line < xb; line++)
+		for (int step = 0; step < H; step++)
+			sgm2_step_ex(sd, line, step, x0, x1, in, out, tmp, H, W, D, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction,
+				     W, yoff, 0, Ht);
 }
 
 void orc_sgm2(const float *x0, const float *x1, const float *in, float *out, float *tmp,

@@ -51,6 +51,9 @@ void orc_sgm2(const float *x0, const float *x1, const float *in, float *out, flo
 void orc_sgm2_band(const float *x0, const float *x1, const float *in, float *out, float *tmp,
 		   int H, int W, int D, int Wt, int yoff, int xoff, float pi1, float pi2, float tau_so, float alpha1,
 		   float sgm_q1, float sgm_q2, int direction, int pass_mask);
+void orc_sgm2_vrows(const float *x0, const float *x1, const float *in, float *out, float *tmp,
+		    int H, int W, int D, int Ht, int yoff, float pi1, float pi2, float tau_so, float alpha1,
+		    float sgm_q1, float sgm_q2, int direction, int sd, int xa, int xb);
 void orc_spatial_argmin(const float *in, float *out, int D, int HW);
 void orc_outlier_detection(const float *d0, const float *d1, float *outlier, int H, int W, int disp_max);
 void orc_interpolate_occlusion(const float *d0, const float *outlier, float *out, int H, int W);

@@ -151,6 +151,19 @@ def sgm2_band(x0, x1, vol_hwd, out, Wt, yoff, xoff, pi1, pi2, tau_so, alpha1, sg
     return out
 
 
+def sgm2_vrows(x0, x1, vol_hwd, out, state, Ht, yoff, pi1, pi2, tau_so, alpha1, sgm_q1, sgm_q2, direction, sd, xa, xb):
+    """one vertical pass (sd 2 down / 3 up) over the row band [yoff, yoff + H) of an Ht-row image, columns [xa, xb);
+    `state` (D, W) float32 carries the line state in and out (the CPU statement of the GPU's chained vertical scans)"""
+    x0, x1 = _f(x0), _f(x1)
+    assert vol_hwd.dtype == np.float32 and vol_hwd.flags["C_CONTIGUOUS"] and out.flags["C_CONTIGUOUS"]
+    assert state.dtype == np.float32 and state.flags["C_CONTIGUOUS"]
+    H, W, D = vol_hwd.shape
+    cf = ctypes.c_float
+    lib().orc_sgm2_vrows(_p(x0), _p(x1), _p(vol_hwd), _p(out), _p(state), H, W, D, int(Ht), int(yoff), cf(pi1), cf(pi2), cf(tau_so),
+                         cf(alpha1), cf(sgm_q1), cf(sgm_q2), int(direction), int(sd), int(xa), int(xb))
+    return out
+
+
 def spatial_argmin(vol):
     vol = _f(vol)
     D, H, W = vol.shape

@@ -149,6 +149,36 @@ def test_sgm2_bands_equal_whole_image(oracle, H, W, D, direction):
     same(acc[None], want, "sgm2 by bands")
 
 
+@pytest.mark.parametrize("H,W,D,direction", [(23, 37, 20, -1), (17, 45, 70, 1), (12, 300, 228, -1)])
+def test_sgm2_rows_chained_over_row_bands(oracle, H, W, D, direction):
+    """mccnn_sgm2_rows: horizontal passes band by band, then each vertical pass as a chain over three row bands and two
+    column chunks with the line state handed from band to band (what rowband.py does across GPUs) == whole-image sgm2"""
+    from mccnn_b200 import rowband
+
+    p = synth.make_pair(H, W, 4, D, seed=5 * D)
+    volL, volR = oracle.stereo_join(p["featL"], p["featR"], D)
+    vol = oracle.transpose_dhw_to_hwd(volL if direction == -1 else volR)
+    opt = pipeline.make_params("kitti", "fast")
+    want = oracle.sgm2(p["imgL"], p["imgR"], vol, opt.pi1, opt.pi2, opt.tau_so, opt.alpha1, opt.sgm_q1, opt.sgm_q2, direction)
+    ops = rowband.CudaOps(dev())
+    iL, iR, cost = cu(p["imgL"]), cu(p["imgR"]), cu(vol)
+    tab = ops.sgm_tables(iL, iR, D, opt, direction)
+    bands = [(0, H // 3), (H // 3, H // 3 + 1), (H // 3 + 1, H)]     # a one-row band in the middle
+    costs = [cost[a:b].contiguous() for a, b in bands]
+    accs = [torch.full_like(c, float("nan")) for c in costs]         # zero_out: need not be initialised
+    for (a, b), c, acc in zip(bands, costs, accs):
+        ops.sgm_rows(tab, c, acc, H, a, opt, direction, 3, True, 0, W, None, None)
+    chunks = [(0, W // 2 + 1), (W // 2 + 1, W)]
+    for sd, order in ((2, [0, 1, 2]), (3, [2, 1, 0])):
+        state = None
+        for i in order:
+            out_state = ops.new_state(W, D, cost) if i != order[-1] else None
+            for xa, xb in chunks:
+                ops.sgm_rows(tab, costs[i], accs[i], H, bands[i][0], opt, direction, 1 << sd, False, xa, xb, state, out_state)
+            state = out_state
+    same(torch.cat(accs)[None], want, "sgm2 chained over row bands")
+
+
 def test_transposes_argmin(oracle):
     D, H, W = 13, 17, 29
     rng = np.random.default_rng(5)
@@ -244,6 +274,21 @@ def test_normalize_ad_census(oracle):
         same(o, oracle.ad(a[0, 0], b[0, 0], 6, direction), "ad")
         adcensus.census(cu(a), cu(b), o, direction)
         same(o, oracle.census(a[0], b[0], 6, direction), "census")
+
+
+@pytest.mark.parametrize("H,W,D,nch", [(15, 27, 6, 1), (40, 300, 70, 1), (9, 140, 150, 3), (21, 131, 17, 3), (5, 7, 9, 2)])
+def test_ad_census_b200_kernels(oracle, H, W, D, nch):
+    """bit-packed census (popcount of XORed 81-bit descriptors) and the shared-memory AD against the oracle's tap loops
+    (adcensus.cu:62-175): bit-identical, borders / D > W / multi-channel included; quantised images force census ties"""
+    rng = np.random.default_rng(H * W + nch)
+    a = np.round(rng.standard_normal((nch, H, W)) * 3).astype(np.float32) / 3
+    b = np.round(rng.standard_normal((nch, H, W)) * 3).astype(np.float32) / 3
+    for direction in (-1, 1):
+        o = torch.empty((1, D, H, W), device=dev())
+        adcensus.census(cu(a)[None], cu(b)[None], o, direction)
+        same(o, oracle.census(a, b, D, direction), "census")
+        adcensus.ad(cu(a[:1])[None], cu(b[:1])[None], o, direction)
+        same(o, oracle.ad(a[0], b[0], D, direction), "ad")
 
 
 PIPE_CASES = [

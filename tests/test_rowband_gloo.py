@@ -1,6 +1,7 @@
-"""CPU, world_size 2 and 3 over gloo: the row-band split of ONE stereo pair (halo exchange before
-every CBCA iteration, all-to-all re-partition around the vertical SGM passes, gathered post-
-processing) with the CPU oracle standing in for the CUDA operators.  The result must equal the
+"""CPU, world_size 2 and 3 over gloo: the row-band split of ONE stereo pair (CBCA blocks on bands extended by
+iterations x halo rows, one halo exchange per block; the vertical SGM passes as a wavefront over column chunks
+that hands only the line state across a band boundary; gathered post-processing) with the CPU oracle standing in
+for the CUDA operators.  The result must equal the
 single-process oracle pipeline bit for bit."""
 import os
 import socket
@@ -55,6 +56,32 @@ class OracleOps:
             a[:] = 0
         self.o.sgm2_band(self._n(imgL), self._n(imgR), c, a, Wt, yoff, xoff, opt.pi1, opt.pi2, opt.tau_so, opt.alpha1,
                          opt.sgm_q1, opt.sgm_q2, direction, pass_mask)
+        acc.copy_(torch.from_numpy(a))
+
+    def sgm_tables(self, imgL, imgR, D, opt, direction):
+        return (self._n(imgL), self._n(imgR))          # the oracle looks the images up directly
+
+    def new_state(self, W, D, like):
+        return torch.zeros((W, D), dtype=torch.float32)
+
+    def sgm_rows(self, tab, cost, acc, Ht, yoff, opt, direction, pass_mask, zero_out, xa, xb, state_in, state_out):
+        iL, iR = tab
+        c, a = self._n(cost), self._n(acc)
+        W = c.shape[1]
+        if zero_out:
+            a[:] = 0
+        args = (opt.pi1, opt.pi2, opt.tau_so, opt.alpha1, opt.sgm_q1, opt.sgm_q2, direction)
+        if pass_mask & 3:
+            self.o.sgm2_band(iL, iR, c, a, W, yoff, 0, *args, pass_mask & 3)
+        for sd in (2, 3):
+            if not pass_mask & (1 << sd):
+                continue
+            st = np.zeros((c.shape[2], W), np.float32)     # the oracle's line state is (D, W)
+            if state_in is not None:
+                st[:, xa:xb] = state_in[xa:xb].numpy().T
+            self.o.sgm2_vrows(iL, iR, c, a, st, Ht, yoff, *args, sd, xa, xb)
+            if state_out is not None:
+                state_out[xa:xb] = torch.from_numpy(np.ascontiguousarray(st[:, xa:xb].T))
         acc.copy_(torch.from_numpy(a))
 
     def argmin(self, vol):

@@ -34,6 +34,7 @@ ap.add_argument("--cbca_i1", type=int, default=None)
 ap.add_argument("--cbca_i2", type=int, default=None)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--chunks", type=int, default=None, help="column chunks of the vertical SGM wavefront")
 ap.add_argument("--cheap-inputs", action="store_true", help="random unit-norm features generated on the device (bench sizes)")
 a = ap.parse_args()
 
@@ -75,14 +76,14 @@ def barrier():
     torch.cuda.synchronize()
 
 
-out = rowband.stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm)   # warm-up (also the result we check)
+out = rowband.stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm, chunks=a.chunks)   # warm-up (also the result we check)
 barrier()
 times = []
 for _ in range(a.iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    out = rowband.stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm)
+    out = rowband.stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm, chunks=a.chunks)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -95,7 +96,7 @@ for _ in range(a.iters):
 res = {"workload": "rowband %dx%d d=%d C=%d %s %s" % (H, W, D, C, a.preset, over), "n_gpus": world,
        "ms_min": round(min(times), 3), "ms_all": [round(x, 3) for x in times], "finite": bool(torch.isfinite(out).all())}
 if a.check and rank == 0:
-    sp = pipeline.StereoPipeline(C, D, H, W, opt, device=local)
+    sp = pipeline.StereoPipeline(C, D, H, W, opt, device=local, cbca_mode="exact")   # the band driver runs the exact operators
     ref = sp.run(featL, featR, imgL, imgR)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
