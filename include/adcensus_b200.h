@@ -66,8 +66,8 @@ int mccnn_stereo_join_pitched(const float *input_L, const float *input_R, float 
 int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1, adcensus_stream_t stream);
 
 /* adcensus.cbca(x0c, x1c, vol_in, vol_out, direction)  adcensus.cu:343-400
- * vol_in must not alias vol_out.  Synchronises `stream` once (it reads back the
- * longest arm to size its shared-memory tile). */
+ * vol_in must not alias vol_out.  Fully asynchronous: the longest arm, which sizes the shared-memory tile, stays on
+ * the device -- every candidate kernel is launched with a gate on it and the ones out of range return immediately. */
 int adcensus_cbca(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 		  int D, int H, int W, int direction, adcensus_stream_t stream);
 

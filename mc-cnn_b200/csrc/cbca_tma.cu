@@ -16,8 +16,8 @@
 //     requires of the innermost coordinate) of every disparity arrives by ONE TMA box
 //     (cp.async.bulk.tensor.3d on the (W, H, D) view of the pitched volume), double-buffered on two
 //     mbarriers: plane d + 2 streams in while d + 1 is processed;
-//   * row prefix sums in place: thread = (row, segment of SEG floats), float4 accesses at a stride that is
-//     conflict-free, segment totals fixed up in a second sweep;
+//   * row prefix sums in place: a warp per row, five consecutive columns per lane, lane totals combined by a
+//     shuffle scan (one read and one write of the tile, bank-conflict free);
 //   * thread = (column, half of the output rows): it walks 2R + 16 tile rows once; per row one LDS of the
 //     right image's arms (window staged once per CTA), one VIMNMX.U16x2 against its own column's arms
 //     (registers), two prefix lookups, and the running (T, N) pair goes into a per-thread shared-memory
@@ -41,7 +41,7 @@ struct CTCfg {
 	static constexpr int HX = (HALO + 3) & ~3;         // left halo in columns: TMA needs a 16-byte aligned start along x
 	static constexpr int TH = CT_TY + 2 * R + 1;       // image rows y0 - HALO .. y0 + TY + R - 1
 	static constexpr int TWMIN = HX + CT_TX + R;       // image columns x0 - HX .. x0 + TX + R - 1
-	static constexpr int SEG = R <= 4 ? 28 : 20;       // floats per prefix segment: SEG / 4 odd => conflict-free float4
+	static constexpr int SEG = R <= 4 ? 28 : 20;       // the tile pitch is a multiple of 20 floats (16-byte rows for TMA, 5 per lane for the row scan)
 	static constexpr int NSEG = (TWMIN + SEG - 1) / SEG;
 	static constexpr int TWP = NSEG * SEG;             // tile pitch = TMA box width (140 / 160 floats)
 	static constexpr int RING = R <= 1 ? 4 : (R <= 7 ? 16 : 32);   // >= 2R + 2 rows of (T, N) per thread
@@ -51,14 +51,13 @@ struct CTCfg {
 	static constexpr int OFF_RING = 2 * STAGE_BYTES;
 	static constexpr int OFF_WINH = OFF_RING + RING * CT_NT * 8;
 	static constexpr int OFF_WINV = OFF_WINH + TH * CT_WW * 4;
-	static constexpr int OFF_TOT = OFF_WINV + ((CT_TY * CT_WW * 2 + 15) & ~15);
-	static constexpr int OFF_BAR = OFF_TOT + ((TH * NSEG * 4 + 15) & ~15);
+	static constexpr int OFF_BAR = OFF_WINV + ((CT_TY * CT_WW * 2 + 15) & ~15);
 	static constexpr int SMEM = OFF_BAR + 16;
 	static_assert(RING >= 2 * R + 2, "ring too small");
 	static_assert(TWP <= 256 && TH <= 256, "TMA box limits");
 };
 
-template <int R>
+template <int R, int WB>
 __global__ void __launch_bounds__(CT_NT, (CTCfg<R>::SMEM <= 112 * 1024) ? 2 : 1)
 cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		const uint32_t *__restrict__ a0h, const uint32_t *__restrict__ a0v,
@@ -67,12 +66,11 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		int D, int H, int W, int ld, int direction, int dch)
 {
 	using C = CTCfg<R>;
-	constexpr int HALO = C::HALO, HX = C::HX, TH = C::TH, TWP = C::TWP, SEG = C::SEG, NSEG = C::NSEG, RING = C::RING, NWALK = C::NWALK;
+	constexpr int HALO = C::HALO, HX = C::HX, TH = C::TH, TWP = C::TWP, RING = C::RING, NWALK = C::NWALK;
 	extern __shared__ __align__(128) unsigned char ct_smem[];
 	float2 *ring = reinterpret_cast<float2 *>(ct_smem + C::OFF_RING);       // [RING][CT_NT] (T, N) per thread
 	uint32_t *winH = reinterpret_cast<uint32_t *>(ct_smem + C::OFF_WINH);   // [TH][CT_WW] right-image H words
 	uint16_t *winV = reinterpret_cast<uint16_t *>(ct_smem + C::OFF_WINV);   // [CT_TY][CT_WW] right-image U | D << 8
-	float *tot = reinterpret_cast<float *>(ct_smem + C::OFF_TOT);           // [TH * NSEG] segment totals
 	uint64_t *bars = reinterpret_cast<uint64_t *>(ct_smem + C::OFF_BAR);
 
 	const int tid = threadIdx.x;
@@ -167,43 +165,34 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		const bool clean = direction < 0 ? (x0 - HX - d < 0) : (x0 + CT_TX + R + d >= W);
 		mbar_wait(&bars[s], (dd >> 1) & 1);
 
-		// 1. inclusive prefix of every tile row, in place
-		for (int it = tid; it < TH * NSEG; it += CT_NT) {
-			float4 *p4 = reinterpret_cast<float4 *>(P + it * SEG);
-			float v[SEG];
+		// 1. inclusive prefix of every tile row, in place: a warp per row, a lane owns EPL consecutive columns (stride-5 word
+		// accesses are bank-conflict free), lane totals combined by a shuffle scan -- one read and one write of the tile
+		{
+			constexpr int EPL = 5, NLN = TWP / EPL;
+			static_assert(TWP % EPL == 0 && NLN <= 32, "row does not fit one warp");
+			const int lane = tid & 31;
+			for (int r = tid >> 5; r < TH; r += CT_NT / 32) {
+				float *row = P + r * TWP + lane * EPL;
+				float v[EPL];
 #pragma unroll
-			for (int i = 0; i < SEG / 4; i++) {
-				const float4 q = p4[i];
-				v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-			}
-			if (clean) {
+				for (int i = 0; i < EPL; i++) v[i] = lane < NLN ? row[i] : 0.0f;
+				if (clean) {
 #pragma unroll
-				for (int i = 0; i < SEG; i++) v[i] = v[i] == v[i] ? v[i] : 0.0f;
-			}
-			float run = 0.0f;
+					for (int i = 0; i < EPL; i++) v[i] = v[i] == v[i] ? v[i] : 0.0f;
+				}
 #pragma unroll
-			for (int i = 0; i < SEG; i++) {
-				run += v[i];
-				v[i] = run;
-			}
+				for (int i = 1; i < EPL; i++) v[i] += v[i - 1];
+				float incl = v[EPL - 1];
 #pragma unroll
-			for (int i = 0; i < SEG / 4; i++) p4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-			tot[it] = run;
-		}
-		__syncthreads();
-		for (int it = tid; it < TH * NSEG; it += CT_NT) {
-			const int seg = it % NSEG;
-			if (seg == 0) continue;
-			float o = 0.0f;
+				for (int o = 1; o < 32; o <<= 1) {
+					const float up = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= o) incl += up;
+				}
+				const float base = incl - v[EPL - 1];
+				if (lane < NLN) {
 #pragma unroll
-			for (int q = 0; q < NSEG - 1; q++)
-				if (q < seg) o += tot[it - seg + q];
-			float4 *p4 = reinterpret_cast<float4 *>(P + it * SEG);
-#pragma unroll
-			for (int i = 0; i < SEG / 4; i++) {
-				float4 q = p4[i];
-				q.x += o; q.y += o; q.z += o; q.w += o;
-				p4[i] = q;
+					for (int i = 0; i < EPL; i++) row[i] = v[i] + base;
+				}
 			}
 		}
 		if (dd == 0) asm volatile("cp.async.wait_group 0;");   // the arm windows of this chunk have landed
@@ -226,7 +215,6 @@ cbca_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 		*reinterpret_cast<float2 *>(rgb) = make_float2(0.0f, __int_as_float(0));   // relative row 0: the excluded row of output 0
 		// rows in batches of WB: all the shared-memory reads of a batch are issued before its (short) serial part, so that
 		// their latency overlaps (the kernel is latency-, not bandwidth-bound at 16 warps per SM)
-		constexpr int WB = 4;
 #pragma unroll
 		for (int b0 = 1; b0 <= NWALK; b0 += WB) {
 			uint32_t hw[WB], vw[WB];
@@ -322,7 +310,7 @@ __global__ void pack_arms_hv_kernel(const float *__restrict__ xc, uint32_t *__re
 	vw[id] = ((uint32_t)u << 8) | ((uint32_t)d << 24);
 }
 
-template <int R>
+template <int R, int WB>
 int launch_tma(const CUtensorMap &tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
 	       cudaStream_t s)
 {
@@ -331,7 +319,7 @@ int launch_tma(const CUtensorMap &tm, const uint32_t *hv, const float *vol, floa
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!attr_done[dev & 63]) {
-		ADC_CUDA(cudaFuncSetAttribute(cbca_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+		ADC_CUDA(cudaFuncSetAttribute(cbca_tma_kernel<R, WB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
 		attr_done[dev & 63] = true;
 	}
 	const char *env = getenv("ADCENSUS_CBCA_DCH");         // tuning knob, not part of the ABI
@@ -340,7 +328,7 @@ int launch_tma(const CUtensorMap &tm, const uint32_t *hv, const float *vol, floa
 	if (dch > CT_DCH) dch = CT_DCH;
 	const long HW = (long)H * W;
 	dim3 grid(adc_div_up(W, CT_TX), adc_div_up(H, CT_TY), adc_div_up(D, dch));
-	cbca_tma_kernel<R><<<grid, CT_NT, C::SMEM, s>>>(tm, hv, hv + 2 * HW, hv + HW, hv + 3 * HW, vol, out, D, H, W, ld, direction, dch);
+	cbca_tma_kernel<R, WB><<<grid, CT_NT, C::SMEM, s>>>(tm, hv, hv + 2 * HW, hv + HW, hv + 3 * HW, vol, out, D, H, W, ld, direction, dch);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
@@ -375,10 +363,15 @@ void adc_cbca_tma_box(int halo, int *box_w, int *box_h)
 int adc_cbca_tma(const CUtensorMap *tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
 		 int halo, cudaStream_t s)
 {
-	if (halo <= 1) return launch_tma<1>(*tm, hv, vol, out, D, H, W, ld, direction, s);
-	if (halo <= 4) return launch_tma<4>(*tm, hv, vol, out, D, H, W, ld, direction, s);
-	if (halo <= 8) return launch_tma<8>(*tm, hv, vol, out, D, H, W, ld, direction, s);
-	if (halo <= 13) return launch_tma<13>(*tm, hv, vol, out, D, H, W, ld, direction, s);
+	if (halo <= 1) return launch_tma<1, 4>(*tm, hv, vol, out, D, H, W, ld, direction, s);
+	if (halo <= 4) {
+		static const int wb = getenv("ADCENSUS_CBCA_WB") ? atoi(getenv("ADCENSUS_CBCA_WB")) : 4;   // tuning knob (rows per walk batch)
+		if (wb == 6) return launch_tma<4, 6>(*tm, hv, vol, out, D, H, W, ld, direction, s);
+		if (wb == 8) return launch_tma<4, 8>(*tm, hv, vol, out, D, H, W, ld, direction, s);
+		return launch_tma<4, 4>(*tm, hv, vol, out, D, H, W, ld, direction, s);
+	}
+	if (halo <= 8) return launch_tma<8, 4>(*tm, hv, vol, out, D, H, W, ld, direction, s);
+	if (halo <= 13) return launch_tma<13, 4>(*tm, hv, vol, out, D, H, W, ld, direction, s);
 	return ADCENSUS_ELIMIT;
 }
 

@@ -127,8 +127,11 @@ struct CWCfg {
 template <int R>
 __global__ void __launch_bounds__(CW_NT, 2)
 cbca_win_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
-		const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int ld, int direction, int dch)
+		const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int ld, int direction, int dch,
+		const int *__restrict__ gate, int gate_lo, int gate_hi)
 {
+	// device-side kernel selection (adcensus_cbca): run only if the longest arm, known on the device, is in this kernel's range
+	if (gate && (*gate < gate_lo || *gate > gate_hi)) return;
 	using Cfg = CWCfg<R>;
 	constexpr int TH = Cfg::TH, TWP = Cfg::TWP, A1W = Cfg::A1W;
 	extern __shared__ __align__(16) uint32_t cw_smem[];
@@ -293,8 +296,10 @@ constexpr int CB_TX = 64, CB_TY = 16, CB_DCH = 16, CB_NT = 256;
 template <int R>  // halo = longest arm - 1
 __global__ void __launch_bounds__(CB_NT)
 cbca_loop_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ a1g,
-		 const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int ld, int direction)
+		 const float *__restrict__ vol, float *__restrict__ out, int D, int H, int W, int ld, int direction,
+		 const int *__restrict__ gate, int gate_lo, int gate_hi)
 {
+	if (gate && (*gate < gate_lo || *gate > gate_hi)) return;
 	constexpr int TH = CB_TY + 2 * R;          // tile rows incl. halo
 	constexpr int TW = CB_TX + 2 * R;          // volume tile columns incl. halo
 	constexpr int A1W = CB_TX + CB_DCH;        // right-image arm window columns
@@ -370,8 +375,10 @@ cbca_loop_kernel(const uint32_t *__restrict__ a0g, const uint32_t *__restrict__ 
 // largest shared-memory halo or the arms are not integer cross() outputs.
 __global__ void cbca_generic_kernel(const float *__restrict__ x0c, const float *__restrict__ x1c,
 				    const float *__restrict__ vol, float *__restrict__ out,
-				    long size, int H, int W, int ld, int direction)
+				    long size, int H, int W, int ld, int direction,
+				    const int *__restrict__ gate, int gate_lo, int gate_hi)
 {
+	if (gate && (*gate < gate_lo || *gate > gate_hi)) return;
 	long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (id >= size) return;
 	long HW = (long)H * W;
@@ -397,7 +404,8 @@ __global__ void cbca_generic_kernel(const float *__restrict__ x0c, const float *
 }
 
 template <int R>
-int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int ld, int direction, cudaStream_t s)
+int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int ld, int direction, cudaStream_t s,
+	       const int *gate = nullptr, int gate_lo = 0, int gate_hi = 0)
 {
 	using Cfg = CWCfg<R>;
 	constexpr int SMEM = Cfg::SMEM;
@@ -416,15 +424,16 @@ int launch_win(const uint32_t *a0, const uint32_t *a1, const float *vol, float *
 	if (dch < 1) dch = 1;
 	if (dch > CW_DCH_MAX) dch = CW_DCH_MAX;
 	dim3 grid(adc_div_up(W, CW_TX), adc_div_up(H, CW_TY), adc_div_up(D, dch));
-	cbca_win_kernel<R><<<grid, CW_NT, SMEM, s>>>(a0, a1, vol, out, D, H, W, ld, direction, dch);
+	cbca_win_kernel<R><<<grid, CW_NT, SMEM, s>>>(a0, a1, vol, out, D, H, W, ld, direction, dch, gate, gate_lo, gate_hi);
 	return 0;
 }
 
 template <int R>
-void launch_tile(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int ld, int direction, cudaStream_t s)
+void launch_tile(const uint32_t *a0, const uint32_t *a1, const float *vol, float *out, int D, int H, int W, int ld, int direction, cudaStream_t s,
+		 const int *gate = nullptr, int gate_lo = 0, int gate_hi = 0)
 {
 	dim3 grid(adc_div_up(W, CB_TX), adc_div_up(H, CB_TY), adc_div_up(D, CB_DCH));
-	cbca_loop_kernel<R><<<grid, CB_NT, 0, s>>>(a0, a1, vol, out, D, H, W, ld, direction);
+	cbca_loop_kernel<R><<<grid, CB_NT, 0, s>>>(a0, a1, vol, out, D, H, W, ld, direction, gate, gate_lo, gate_hi);
 }
 
 }  // namespace
@@ -460,7 +469,7 @@ int adc_cbca_packed(const uint32_t *pk, const float *x0c, const float *x1c,
 	else if (halo <= 13) launch_tile<13>(a0, a1, vol, out, D, H, W, ld, direction, s);
 	else {
 		long size = (long)D * H * W;
-		cbca_generic_kernel<<<adc_div_up(size, 256), 256, 0, s>>>(x0c, x1c, vol, out, size, H, W, ld, direction);
+		cbca_generic_kernel<<<adc_div_up(size, 256), 256, 0, s>>>(x0c, x1c, vol, out, size, H, W, ld, direction, nullptr, 0, 0);
 	}
 	ADC_CHECK_LAUNCH();
 	return 0;
@@ -526,18 +535,28 @@ extern "C" int adcensus_cbca(const float *x0c, const float *x1c, const float *vo
 	if (!x0c || !x1c || !vol_in || !vol_out || vol_in == vol_out) return ADCENSUS_EINVAL;
 	if (D < 1 || H < 1 || W < 1 || (direction != 1 && direction != -1)) return ADCENSUS_EINVAL;
 	cudaStream_t s = adc_stream(stream);
-	long HW = (long)H * W;
+	const long HW = (long)H * W;
 	uint32_t *packed = nullptr;
 	int rc = adc_scratch_alloc((void **)&packed, (adc_packed_words(H, W) + 1) * sizeof(uint32_t), s);
 	if (rc) return rc;
 	int *maxlen_dev = (int *)(packed + adc_packed_words(H, W));
-	int maxlen = 0;
 	rc = (int)cudaMemsetAsync(maxlen_dev, 0, sizeof(int), s);
 	if (!rc) rc = adc_pack_arms(x0c, packed, 0, H, W, maxlen_dev, s);
 	if (!rc) rc = adc_pack_arms(x1c, packed, 1, H, W, maxlen_dev, s);
-	if (!rc) rc = (int)cudaMemcpyAsync(&maxlen, maxlen_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
-	if (!rc) rc = (int)cudaStreamSynchronize(s);
-	if (!rc) rc = adc_cbca_packed(packed, x0c, x1c, vol_in, vol_out, D, H, W, W, direction, maxlen, s);
+	if (!rc) {
+		// The longest arm is only known on the device.  Instead of reading it back (a host synchronisation per call),
+		// every candidate kernel is launched with a gate on that device value; the ones out of range return at once.
+		const uint32_t *a0 = packed, *a1 = packed + HW;
+		rc = launch_win<1>(a0, a1, vol_in, vol_out, D, H, W, W, direction, s, maxlen_dev, 0, 2);
+		if (!rc) rc = launch_win<4>(a0, a1, vol_in, vol_out, D, H, W, W, direction, s, maxlen_dev, 3, 5);
+		if (!rc) {
+			launch_tile<8>(a0, a1, vol_in, vol_out, D, H, W, W, direction, s, maxlen_dev, 6, 9);
+			launch_tile<13>(a0, a1, vol_in, vol_out, D, H, W, W, direction, s, maxlen_dev, 10, 14);
+			const long size = (long)D * H * W;
+			cbca_generic_kernel<<<adc_div_up(size, 256), 256, 0, s>>>(x0c, x1c, vol_in, vol_out, size, H, W, W, direction, maxlen_dev, 15, 1 << 30);
+			rc = (int)cudaPeekAtLastError();
+		}
+	}
 	int rc2 = adc_scratch_free(packed, s);
 	return rc ? rc : rc2;
 }

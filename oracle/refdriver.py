@@ -113,10 +113,11 @@ def fix_border(vol, n, direction):
             vol[:, :, :, W - i].copy_(vol[:, :, :, W - n - 1])
 
 
-def stereo_predict(shim, x_batch, features, opt, disp_max, want_vols=False, stages=None):
+def stereo_predict(shim, x_batch, features, opt, disp_max, want_vols=False, stages=None, directions=(1, -1)):
     """main.lua:929-1082 (arch 'fast') with every adcensus.* call going to `shim`.
 
-    `stages`, when a dict, receives clones of the intermediate tensors (for fixtures).
+    `stages`, when a dict, receives clones of the intermediate tensors (for fixtures).  `directions`: main.lua:954-955 runs
+    {1, -1}, or {-1} alone for dataset 'mb' outside `-a predict` (then the right volume is never aggregated).
     """
     call = shim.call
     H, W = x_batch.size(2), x_batch.size(3)
@@ -131,7 +132,7 @@ def stereo_predict(shim, x_batch, features, opt, disp_max, want_vols=False, stag
     disp = {}
     out_vols = {}
     vol = None
-    for direction in (1, -1):                                                               # :955
+    for direction in directions:                                                            # :954-955
         tag = "L" if direction == -1 else "R"
         vol = vols[0:1] if direction == -1 else vols[1:2]                                   # :986
         x0c = torch.empty((1, 4, H, W), device=dev, dtype=torch.float32)
@@ -163,7 +164,9 @@ def stereo_predict(shim, x_batch, features, opt, disp_max, want_vols=False, stag
         d = torch.empty((1, 1, H, W), device=dev, dtype=torch.float32)
         call("spatial_argmin", vol, d)                                                      # :1049
         disp[1 if direction == 1 else 2] = d.add_(-1)                                       # :1050
-    rec("disp_R", disp[1]); rec("disp_L", disp[2])
+    if 1 in disp:
+        rec("disp_R", disp[1])
+    rec("disp_L", disp[2])
     d = disp[2]
     if opt.lr_check:                                                                        # :1054-1066
         outlier = torch.zeros_like(d)
@@ -180,5 +183,5 @@ def stereo_predict(shim, x_batch, features, opt, disp_max, want_vols=False, stag
     d = call("mean2d", d, gaussian(opt.blur_sigma).to(dev), opt.blur_t)[0]                  # :1078
     rec("disp", d)
     if want_vols:
-        return d, out_vols[-1], out_vols[1]
+        return d, out_vols[-1], out_vols.get(1)
     return d

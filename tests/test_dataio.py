@@ -1,4 +1,6 @@
 """CPU: the data formats either side of the hot path (mc-cnn_b200/dataio.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -87,3 +89,46 @@ def test_kitti_submission_image_and_file(tmp_path):
     f = dataio.write_kitti_submission(pred, 5, 4, str(tmp_path / "out"), 7, "kitti2015")
     assert f.endswith("disp_0/000007_10.png")
     assert np.array_equal(dataio.read_png16(f), img)
+
+
+# ---- pinned against the reference's own Python (fixtures: oracle/make_dataio_golden.py ran /root/reference/preprocess_mb.py's code)
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataio")
+
+
+def test_fromfile_reads_what_the_reference_tofile_wrote():
+    """tests/golden/dataio/*.bin(+.dim,.type) were written by preprocess_mb.py:99-106 itself"""
+    want = np.load(os.path.join(GOLD, "expected.npz"))
+    for name in ("x_f32", "te_i32", "meta_i32"):
+        got = dataio.fromfile(os.path.join(GOLD, name + ".bin"))
+        assert got.dtype == want[name].dtype and got.shape == want[name].shape
+        assert np.array_equal(got, want[name]), name
+    assert dataio.fromfile(os.path.join(GOLD, "none.bin")).size == 0          # '.dim' holding the single line 0
+
+
+def test_tofile_writes_the_same_bytes_as_the_reference(tmp_path):
+    want = np.load(os.path.join(GOLD, "expected.npz"))
+    for name in ("x_f32", "te_i32", "meta_i32"):
+        f = str(tmp_path / (name + ".bin"))
+        dataio.tofile(f, want[name])
+        for ext in ("", ".dim", ".type"):
+            assert open(f + ext, "rb").read() == open(os.path.join(GOLD, name + ".bin" + ext), "rb").read(), name + ext
+    f = str(tmp_path / "none.bin")
+    dataio.tofile(f, None)
+    assert open(f + ".dim", "rb").read() == open(os.path.join(GOLD, "none.bin.dim"), "rb").read()
+
+
+def test_read_pfm_agrees_with_the_reference_reader():
+    """disp.pfm as parsed by preprocess_mb.py:13-57 (load_pfm returns the rows top-down: np.flipud of the file order)"""
+    ref = np.load(os.path.join(GOLD, "disp_pfm_as_read_by_reference.npy"))
+    got = dataio.read_pfm(os.path.join(GOLD, "disp.pfm"))
+    assert np.array_equal(np.flipud(got), ref)
+
+
+def test_bin_layout_is_what_samples_load_bin_reads(tmp_path):
+    """samples/load_bin.py: np.memmap(name, float32, shape=(1, D, H, W)) -- plain C-order float32, no header"""
+    D, H, W = 3, 4, 5
+    vol = np.arange(D * H * W, dtype=np.float32).reshape(1, D, H, W)
+    f = str(tmp_path / "left.bin")
+    vol.tofile(f)
+    back = np.memmap(f, dtype=np.float32, shape=(1, D, H, W))
+    assert np.array_equal(back, vol)

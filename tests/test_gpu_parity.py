@@ -432,6 +432,74 @@ def test_against_live_reference():
         sp.close()
 
 
+@pytest.mark.parametrize("H,W,C,D,preset,over", [
+    (370, 1226, 64, 228, ("kitti", "accurate_cbca4"), {}),      # BASELINE config 3, the bench workload
+    (370, 1226, 64, 70, ("kitti2015", "slow"), {}),             # d = 70 with CBCA x 6 (cbca_i1 = 2, cbca_i2 = 4)
+])
+def test_full_size_default_mode_against_live_reference(H, W, C, D, preset, over):
+    """The pipeline's DEFAULT mode (constant-work CBCA) at BASELINE.json's full size against the reference's own kernels on
+    the same box, with SURVEY.md 8(d)'s fast-mode thresholds: volumes |a - b| <= 1e-4 * max(1, |b|) with identical NaN
+    pattern; disp.bin within 1e-4 on >= (1 - 1e-4) of the pixels."""
+    from oracle import refdriver
+
+    if not os.path.exists(refdriver.REF_LIB):
+        pytest.skip("oracle/_ref/libadcensus_ref.so not present")
+    shim = refdriver.ShimLibrary(refdriver.REF_LIB)
+    opt = pipeline.make_params(*preset, **over)
+    p = synth.make_pair(H, W, C, D, seed=2)
+    x_batch = cu(np.stack([p["imgL"], p["imgR"]])[:, None])
+    feats = cu(np.stack([p["featL"], p["featR"]]))
+    want, wL, wR = refdriver.stereo_predict(shim, x_batch, feats, opt, D, want_vols=True)
+    sp = pipeline.StereoPipeline(C, D, H, W, opt)
+    assert sp.cbca_mode == "fast"
+    volL = torch.empty((D, H, W), device=dev())
+    volR = torch.empty((D, H, W), device=dev())
+    disp = sp.run(feats[0], feats[1], x_batch[0, 0], x_batch[1, 0], volL=volL, volR=volR)
+    torch.cuda.synchronize()
+    for got, ref, what in ((volL, wL[0], "left.bin"), (volR, wR[0], "right.bin")):
+        assert bool((torch.isnan(got) == torch.isnan(ref)).all()), what + ": NaN pattern differs from the reference"
+        ok = torch.isnan(ref) | ((got - ref).abs() <= 1e-4 * ref.abs().clamp(min=1.0))
+        err = torch.where(torch.isnan(ref), torch.zeros_like(ref), (got - ref).abs() / ref.abs().clamp(min=1.0)).max().item()
+        assert bool(ok.all()), "%s: max relative error %.3g above 1e-4" % (what, err)
+    ref_d = want[0, 0]
+    frac = float(((disp - ref_d).abs() > 1e-4 * ref_d.abs().clamp(min=1.0)).float().mean().item())
+    assert frac <= 1e-4, "disp.bin: %.3g of the pixels differ by more than 1e-4 (bar 1e-4 of the pixels)" % frac
+    sp.close()
+
+
+def test_middlebury_size_against_live_reference():
+    """BASELINE.json config 5's volume on ONE GPU (the scaling denominator of the row-band split): 2000 x 3000, d = 400,
+    'mb fast' preset (main.lua:281-293: no CBCA, no LR check, direction -1 only), exact pipeline against the reference's
+    kernels: left.bin and disp.bin bit for bit."""
+    from oracle import refdriver
+
+    if not os.path.exists(refdriver.REF_LIB):
+        pytest.skip("oracle/_ref/libadcensus_ref.so not present")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 120e9:
+        pytest.skip("needs ~110 GB of device memory")
+    H, W, C, D = 2000, 3000, 64, 400
+    opt = pipeline.make_params("mb", "fast")
+    g = torch.Generator(device=dev()).manual_seed(3)
+    fL = torch.nn.functional.normalize(torch.randn((C, H, W), device=dev(), generator=g), dim=0)
+    fR = torch.nn.functional.normalize(torch.randn((C, H, W), device=dev(), generator=g), dim=0)
+    rng = np.random.default_rng(3)
+    img = synth.natural_image(rng, H, W + 16)
+    st = lambda x: cu(((x - x.mean()) / x.std(ddof=1)).astype(np.float32))
+    iL, iR = st(img[:, 16:]).contiguous(), st(img[:, :W]).contiguous()
+    sp = pipeline.StereoPipeline(C, D, H, W, opt, cbca_mode="exact")
+    volL = torch.empty((D, H, W), device=dev())
+    disp = sp.run(fL, fR, iL, iR, volL=volL)
+    torch.cuda.synchronize()
+    sp.close()
+    shim = refdriver.ShimLibrary(refdriver.REF_LIB)
+    want, wL, _ = refdriver.stereo_predict(shim, torch.stack([iL, iR])[:, None], torch.stack([fL, fR]), opt, D, want_vols=True,
+                                           directions=(-1,))
+    for got, ref, what in ((volL, wL[0], "left.bin"), (disp, want[0, 0], "disp.bin")):
+        bad = ~((got == ref) | (torch.isnan(got) & torch.isnan(ref)))
+        assert int(bad.sum()) == 0, "%s: %d elements differ from the reference at Middlebury size" % (what, int(bad.sum()))
+
+
 FULL_SIZE = [
     # BASELINE.json config 2 (KITTI fast, d=70) and config 3 (KITTI accurate, d=228, CBCA x4 + SGM)
     (370, 1226, 64, 70, ("kitti", "fast"), {}),
