@@ -347,13 +347,25 @@ int adc_pack_arms_hv(const float *xc, uint32_t *hv, int which, int H, int W, cud
 	return 0;
 }
 
+// second-generation kernel for short arms (cbca_ws.cu); ADCENSUS_CBCA_WS=0 keeps the first-generation one
+int adc_cbca_ws_max_halo();
+void adc_cbca_ws_box(int halo, int *box_w, int *box_h);
+int adc_cbca_ws(const CUtensorMap *tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
+		int halo, cudaStream_t s);
+static bool use_ws(int halo)
+{
+	static const int ws = getenv("ADCENSUS_CBCA_WS") ? atoi(getenv("ADCENSUS_CBCA_WS")) : 1;
+	return ws && halo <= adc_cbca_ws_max_halo();
+}
+
 // largest support radius (longest arm - 1) the constant-work kernel is instantiated for
 int adc_cbca_tma_max_halo() { return 13; }
 
 // box of the tensor map a volume needs for support radius `halo` (= longest arm - 1)
 void adc_cbca_tma_box(int halo, int *box_w, int *box_h)
 {
-	if (halo <= 1) { *box_w = CTCfg<1>::TWP; *box_h = CTCfg<1>::TH; }
+	if (use_ws(halo)) adc_cbca_ws_box(halo, box_w, box_h);
+	else if (halo <= 1) { *box_w = CTCfg<1>::TWP; *box_h = CTCfg<1>::TH; }
 	else if (halo <= 4) { *box_w = CTCfg<4>::TWP; *box_h = CTCfg<4>::TH; }
 	else if (halo <= 8) { *box_w = CTCfg<8>::TWP; *box_h = CTCfg<8>::TH; }
 	else { *box_w = CTCfg<13>::TWP; *box_h = CTCfg<13>::TH; }
@@ -363,6 +375,7 @@ void adc_cbca_tma_box(int halo, int *box_w, int *box_h)
 int adc_cbca_tma(const CUtensorMap *tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
 		 int halo, cudaStream_t s)
 {
+	if (use_ws(halo)) return adc_cbca_ws(tm, hv, vol, out, D, H, W, ld, direction, halo, s);
 	if (halo <= 1) return launch_tma<1, 4>(*tm, hv, vol, out, D, H, W, ld, direction, s);
 	if (halo <= 4) {
 		static const int wb = getenv("ADCENSUS_CBCA_WB") ? atoi(getenv("ADCENSUS_CBCA_WB")) : 4;   // tuning knob (rows per walk batch)

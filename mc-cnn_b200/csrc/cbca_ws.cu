@@ -1,0 +1,484 @@
+// cbca_ws.cu -- constant-work cross-based cost aggregation (adcensus.cbca, adcensus.cu:343-400), second generation:
+// warp-specialised, three-stage TMA pipeline, vertical sums in registers.
+//
+// Same decomposition as cbca_tma.cu -- the run of a support row depends on (d, row, column) only, so with I the
+// inclusive prefix of a tile row
+//     S(r, x) = I(r, x + R_ - 1) - I(r, x - L)          sum of the run (x - L, x + R_) of row r        (:362-369)
+//     out(y, x) = sum_{r = y-U+1}^{y+Dn-1} S(r, x) / sum of the run lengths                            (:361, :373)
+// -- but the work is split by ROLE instead of by phase, and the vertical part no longer goes through memory:
+//   * one PRODUCER thread keeps three plane tiles in flight (cp.async.bulk.tensor.3d, one box of 144 x (64 + 2R + 1)
+//     floats per disparity, zero-filled outside the image) behind full / ready / empty mbarriers;
+//   * four PREFIX warps turn each landed tile into row prefixes in place: two tile rows per warp instruction
+//     (16 lanes x 9 consecutive columns each, bank-conflict free at the 144-float pitch), two such pairs interleaved
+//     (the scan is a chain of dependent adds and shuffles), a 4-step shuffle scan,
+//     optionally centred on one value per tile so that |I| stays a random walk instead of growing with the mean
+//     (less cancellation in the differences);
+//   * eight WALKER warps: thread = (column, half of the 64 output rows).  A thread walks 32 + 2R tile rows once;
+//     per row one LDS of the right image's arms, one packed 16-bit minimum against its own column's arms (registers
+//     for the whole disparity chunk), two prefix look-ups -> (S, run length) as a packed f32x2 that stays in
+//     registers for the 2R + 1 outputs whose vertical range can contain the row.  An output is 2R + 1 predicated
+//     add.rn.f32x2 in ascending row order (the reference's row order), a reciprocal with one Newton step, one store.
+//     No per-thread ring in shared memory, no block-wide barrier in the steady state.
+// Compared with cbca_tma.cu (32-row tiles, 2 CTAs per SM, prefix and walk as barrier-separated phases, (T, N) ring in
+// shared memory): 40 % fewer shared-memory wavefronts per output, 64-row tiles (halo overhead 1.25 instead of 1.4 / 1.5),
+// and no cancellation in the vertical direction.  NOT bit-exact by construction (1e-4 contract; measured ~1e-7).
+// Arms up to 5 pixels (R <= 4, the KITTI presets); longer arms stay on cbca_tma.cu / the exact kernels.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace {
+
+constexpr int WS_TX = 128, WS_TY = 64, WS_HO = 32;
+constexpr int WS_NWT = 256;                 // walker threads (8 warps)
+__host__ __device__ constexpr int ws_nt(int npw) { return WS_NWT + 32 * npw + 32; }   // walkers + prefix warps + one producer warp
+constexpr int WS_DCH = 20;                  // max disparities per CTA
+constexpr int WS_WW = WS_TX + WS_DCH;       // pitch of the right-image arm windows
+constexpr int WS_NST = 3;                   // tile stages
+constexpr int WS_TWP = 144;                 // tile pitch = TMA box width: 16 lanes x 9 columns, = 16 (mod 32)
+
+template <int R>
+struct WSCfg {
+	static constexpr int HALO = R + 1;                 // the prefix differences index the first EXCLUDED pixel
+	static constexpr int HX = (HALO + 3) & ~3;         // left halo in columns (TMA: 16-byte aligned start along x)
+	static constexpr int TH = WS_TY + 2 * R + 1;       // image rows y0 - HALO .. y0 + TY + R - 1
+	static constexpr int NWALK = 2 * R + WS_HO;        // rows a thread walks for its 32 outputs
+	static constexpr int TILE_BYTES = TH * WS_TWP * 4; // bytes one TMA box delivers
+	static constexpr int STAGE_BYTES = (TILE_BYTES + 127) & ~127;
+	static constexpr int OFF_WINH = WS_NST * STAGE_BYTES;
+	static constexpr int OFF_WINV = OFF_WINH + TH * WS_WW * 4;
+	static constexpr int OFF_MU = OFF_WINV + ((WS_TY * WS_WW * 2 + 15) & ~15);
+	static constexpr int OFF_BAR = OFF_MU + 16;
+	static constexpr int OFF_RING = OFF_BAR + ((3 * WS_NST * 8 + 15) & ~15);   // VMODE 2 only: [16][WS_NWT] (T, N) per thread
+	static constexpr int RING = 16;
+	static constexpr int SMEM_NORING = OFF_RING;
+	static constexpr int SMEM_RING = OFF_RING + RING * WS_NWT * 8;
+	static_assert(RING >= 2 * R + 2, "ring too small");
+	static_assert(HX + WS_TX + R <= WS_TWP, "tile pitch too small");
+	static_assert(TH <= 256, "TMA box limit");
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned long long ws_pack2(float lo, float hi)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void ws_unpack2(unsigned long long v, float &lo, float &hi)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ws_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+	unsigned long long d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+__device__ __forceinline__ unsigned long long ws_add2(unsigned long long a, unsigned long long b)
+{
+	unsigned long long d;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+
+// CENTER: subtract one value per tile (the tile's mid pixel, 0 when that is not finite) before the row prefix and add
+// it back per run (mu * length): the prefixes then carry deviations instead of the level of the plane.
+// VMODE: how an output gathers its rows y - U + 1 .. y + Dn - 1:
+//   1  2R + 1 fma.rn.f32x2 with a 0/1 float mask per row (mask = saturate(arm - j): one FADD.SAT)
+//   2  running (T, N) down the column in a per-thread shared-memory ring, output = difference of two entries (fewest
+//      instructions, most shared-memory traffic); with CENTER the running sums carry deviations only
+// (predicated add.rn.f32x2 was tried first: ptxas turns each into FADD2 + 2 SEL, 70 instructions per output)
+template <int R, int WB, bool CENTER, int VMODE, int WS_NPW>
+__global__ void __launch_bounds__(ws_nt(WS_NPW), 1)
+cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
+	       const uint32_t *__restrict__ a0h, const uint32_t *__restrict__ a0v,
+	       const uint32_t *__restrict__ a1h, const uint32_t *__restrict__ a1v,
+	       const float *__restrict__ vol, float *__restrict__ out,
+	       int D, int H, int W, int ld, int direction, int dch)
+{
+	using C = WSCfg<R>;
+	constexpr int WS_NT = ws_nt(WS_NPW);
+	constexpr int HALO = C::HALO, HX = C::HX, TH = C::TH, NWALK = C::NWALK, TWP = WS_TWP;
+	extern __shared__ __align__(128) unsigned char ws_smem[];
+	uint32_t *winH = reinterpret_cast<uint32_t *>(ws_smem + C::OFF_WINH);   // [TH][WS_WW] right-image H words
+	uint16_t *winV = reinterpret_cast<uint16_t *>(ws_smem + C::OFF_WINV);   // [WS_TY][WS_WW] right-image U | D << 8
+	float *mus = reinterpret_cast<float *>(ws_smem + C::OFF_MU);            // [WS_NST] centre value of the stage's tile
+	uint64_t *bar_full = reinterpret_cast<uint64_t *>(ws_smem + C::OFF_BAR);   // TMA landed
+	uint64_t *bar_ready = bar_full + WS_NST;                                   // prefixes done
+	uint64_t *bar_empty = bar_ready + WS_NST;                                  // walkers done
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int x0 = blockIdx.x * WS_TX, y0 = blockIdx.y * WS_TY, d0 = blockIdx.z * dch;
+	const int dn = min(dch, D - d0);
+	const int a1x0 = direction > 0 ? x0 + d0 : x0 - (d0 + dch - 1);   // image column of window column 0
+
+	// disparities whose tile is not entirely inside the invalid triangle form a prefix of the chunk (:353-354)
+	int nproc = 0;
+	while (nproc < dn && !(direction < 0 ? (x0 + WS_TX - 1 - (d0 + nproc) < 0) : (x0 + d0 + nproc >= W))) nproc++;
+
+	if (tid == 0) {
+#pragma unroll
+		for (int s = 0; s < WS_NST; s++) {
+			mbar_init(&bar_full[s], 1);
+			mbar_init(&bar_ready[s], WS_NPW);
+			mbar_init(&bar_empty[s], WS_NWT / 32);
+		}
+		mbar_fence_init();
+		tma_prefetch_desc(&tmap);
+	}
+	__syncthreads();
+
+	constexpr int W_PROD = WS_NWT / 32 + WS_NPW;       // producer warp index
+	if (warp == W_PROD && lane == 0) {                 // the first tiles fly while the arm windows are staged
+#pragma unroll
+		for (int s = 0; s < WS_NST; s++)
+			if (s < nproc) {
+				mbar_arrive_expect_tx(&bar_full[s], C::TILE_BYTES);
+				tma_load_3d(ws_smem + s * C::STAGE_BYTES, &tmap, x0 - HX, y0 - HALO, d0 + s, &bar_full[s]);
+			}
+	}
+
+	// right-image arm windows (once per CTA), 0 outside the image: a warp per window row, lanes along x
+	{
+		constexpr int NW = WS_NT / 32, NCH = (WS_WW + 31) / 32;
+		for (int r = warp; r < TH; r += NW) {
+			const int yy = y0 - HALO + r;
+			const bool rowok = yy >= 0 && yy < H;
+			const uint32_t *grow = a1h + (long)(rowok ? yy : 0) * W;
+#pragma unroll
+			for (int m = 0; m < NCH; m++) {
+				const int j = lane + 32 * m, xx = a1x0 + j;
+				if (j < WS_WW) {
+					const bool ok = rowok && xx >= 0 && xx < W;
+					const unsigned dst = (unsigned)__cvta_generic_to_shared(winH + r * WS_WW + j);
+					const int nbytes = ok ? 4 : 0;
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(grow + (ok ? xx : 0)), "r"(nbytes));
+				}
+			}
+		}
+		asm volatile("cp.async.commit_group;");
+		for (int r = warp; r < WS_TY; r += NW) {
+			const int yy = y0 + r;
+			const uint32_t *grow = a1v + (long)(yy < H ? yy : 0) * W;
+			uint32_t v[NCH];
+#pragma unroll
+			for (int m = 0; m < NCH; m++) {
+				const int xx = a1x0 + lane + 32 * m;
+				v[m] = (yy < H && xx >= 0 && xx < W) ? __ldg(grow + xx) : 0u;
+			}
+#pragma unroll
+			for (int m = 0; m < NCH; m++) {
+				const int j = lane + 32 * m;
+				if (j < WS_WW) winV[r * WS_WW + j] = (uint16_t)(((v[m] >> 8) & 255u) | ((v[m] >> 16) & 0xff00u));   // U | D << 8
+			}
+		}
+		asm volatile("cp.async.wait_group 0;");
+	}
+	__syncthreads();                                   // windows visible to the walkers
+
+	if (warp == W_PROD) {
+		// ---------------------------------------------------------------- producer
+		if (lane == 0) {
+			for (int dd = WS_NST; dd < nproc; dd++) {
+				const int s = dd % WS_NST, k = dd / WS_NST;
+				mbar_wait(&bar_empty[s], (k - 1) & 1);          // the walkers are done with plane dd - NST
+				mbar_arrive_expect_tx(&bar_full[s], C::TILE_BYTES);
+				tma_load_3d(ws_smem + s * C::STAGE_BYTES, &tmap, x0 - HX, y0 - HALO, d0 + dd, &bar_full[s]);
+			}
+		}
+		return;
+	}
+
+	if (warp >= WS_NWT / 32) {
+		// ---------------------------------------------------------------- prefix warps
+		constexpr int EPL = 9;
+		static_assert(EPL * 16 == TWP, "two rows per warp: 16 lanes x 9 columns");
+		const int pw = warp - WS_NWT / 32;
+		const int half = lane >> 4, li = lane & 15;
+		for (int dd = 0; dd < nproc; dd++) {
+			const int s = dd % WS_NST, d = d0 + dd;
+			float *P = reinterpret_cast<float *>(ws_smem + s * C::STAGE_BYTES);
+			// does the tile hold entries of the invalid triangle (NaN)?  They never lie inside a run, but a prefix
+			// sum would carry them along the row: count them as 0.
+			const bool scrub = direction < 0 ? (x0 - HX - d < 0) : (x0 - HX + TWP + d > W);
+			mbar_wait(&bar_full[s], (dd / WS_NST) & 1);
+			float mu = 0.0f;
+			if (CENTER) {
+				const float m = P[(HALO + WS_TY / 2) * TWP + HX + WS_TX / 2];
+				mu = (fabsf(m) <= 3.0e38f) ? m : 0.0f;               // finite (NaN and inf fail the compare)
+				if (pw == 0 && lane == 0) mus[s] = mu;
+				asm volatile("bar.sync 1, %0;" ::"n"(32 * WS_NPW) : "memory");   // every prefix warp has read it before any row is rewritten
+			}
+			// two independent row pairs per iteration (the scan of one is a chain of dependent adds and shuffles: a single
+			// pair per iteration left the prefix warps latency-bound and the walkers waiting for them)
+			for (int pr0 = pw; pr0 < (TH + 1) / 2; pr0 += 2 * WS_NPW) {
+				float v[2][EPL];
+				float *row[2];
+				bool act[2];
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					const int r = 2 * (pr0 + u * WS_NPW) + half;
+					act[u] = r < TH;
+					row[u] = P + (act[u] ? r : 0) * TWP + li * EPL;
+#pragma unroll
+					for (int i = 0; i < EPL; i++) v[u][i] = row[u][i];
+				}
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					if (CENTER) {
+#pragma unroll
+						for (int i = 0; i < EPL; i++) v[u][i] -= mu;
+					}
+					if (scrub) {
+#pragma unroll
+						for (int i = 0; i < EPL; i++) v[u][i] = v[u][i] == v[u][i] ? v[u][i] : 0.0f;
+					}
+				}
+#pragma unroll
+				for (int i = 1; i < EPL; i++) {
+					v[0][i] += v[0][i - 1];
+					v[1][i] += v[1][i - 1];
+				}
+				float incl0 = v[0][EPL - 1], incl1 = v[1][EPL - 1];
+#pragma unroll
+				for (int o = 1; o < 16; o <<= 1) {
+					const float up0 = __shfl_up_sync(0xffffffffu, incl0, o, 16);
+					const float up1 = __shfl_up_sync(0xffffffffu, incl1, o, 16);
+					if (li >= o) {
+						incl0 += up0;
+						incl1 += up1;
+					}
+				}
+				const float base0 = incl0 - v[0][EPL - 1], base1 = incl1 - v[1][EPL - 1];
+				if (act[0]) {
+#pragma unroll
+					for (int i = 0; i < EPL; i++) row[0][i] = v[0][i] + base0;
+				}
+				if (act[1]) {
+#pragma unroll
+					for (int i = 0; i < EPL; i++) row[1][i] = v[1][i] + base1;
+				}
+			}
+			fence_proxy_async_smem();                      // generic writes of this stage before its next TMA refill
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&bar_ready[s]);
+		}
+		return;
+	}
+
+	// -------------------------------------------------------------------- walkers
+	const int c = tid & (WS_TX - 1), h = tid >> 7;      // column, half (output rows 32h .. 32h + 31)
+	const int x = x0 + c;
+	const int yb = y0 + WS_HO * h;                       // first output row of this thread
+	const int nv = x < W ? max(0, min(WS_HO, H - yb)) : 0;   // output rows of this thread inside the image
+	// this thread's own column of the left image's arms: registers for the whole chunk
+	uint32_t ah[NWALK], av[WS_HO];
+#pragma unroll
+	for (int w = 0; w < NWALK; w++) {
+		const int yy = yb - HALO + 1 + w;
+		ah[w] = (x < W && yy >= 0 && yy < H) ? __ldg(a0h + (long)yy * W + x) : 0u;
+	}
+#pragma unroll
+	for (int k = 0; k < WS_HO; k++) {
+		const int yy = yb + k;
+		av[k] = (x < W && yy < H) ? __ldg(a0v + (long)yy * W + x) : 0u;
+	}
+
+	for (int dd = 0; dd < nproc; dd++) {
+		const int d = d0 + dd, s = dd % WS_NST;
+		const float *P = reinterpret_cast<const float *>(ws_smem + s * C::STAGE_BYTES);
+		const int sh = d * direction;
+		const int xs = x + sh;
+		const bool valid_col = x < W && xs >= 0 && xs < W;
+		const int off = (x0 + sh) - a1x0;                 // window column of tile column 0
+		mbar_wait(&bar_ready[s], (dd / WS_NST) & 1);
+		const float mu = CENTER ? mus[s] : 0.0f;
+
+		// column walk: relative row rr <-> tile row 32h + rr <-> image row yb - HALO + rr
+		const char *Pc = reinterpret_cast<const char *>(P + (WS_HO * h) * TWP + c + HX);   // own pixel's prefix entry, relative row 0
+		const uint32_t *wh = winH + (WS_HO * h) * WS_WW + c + off;
+		const uint16_t *wv = winV + (WS_HO * h) * WS_WW + c + off;
+		char *po = reinterpret_cast<char *>(out + ((long)d * H + yb) * ld + x);
+		const long ldb = (long)ld * 4;
+		const int nst = valid_col ? nv : 0;                          // rows this thread stores from the walk
+		unsigned long long sn[NWALK + 1];                            // (S, run length) of relative rows 1 .. NWALK
+		constexpr int RROW = WS_NWT * 8;                             // ring row pitch in bytes (VMODE 2)
+		char *rgb = reinterpret_cast<char *>(ws_smem + C::OFF_RING) + tid * 8;
+		unsigned long long run = ws_pack2(0.0f, 0.0f);
+		if (VMODE == 2) *reinterpret_cast<unsigned long long *>(rgb) = run;   // relative row 0: the excluded row of output 0
+		// rows in batches of WB: all the shared-memory reads of a batch are issued before its arithmetic
+#pragma unroll
+		for (int b0 = 1; b0 <= NWALK; b0 += WB) {
+			uint32_t hw[WB], vw[WB];
+			float ph[WB], pl[WB];
+#pragma unroll
+			for (int i = 0; i < WB; i++) {
+				const int rr = b0 + i;
+				if (rr <= NWALK) {
+					hw[i] = __vminu2(ah[rr - 1], wh[rr * WS_WW]);   // min of lengths = (max of left ends, min of right ends), :362-363
+					if (rr >= 2 * R + 1) {
+						const int k = rr - 2 * R - 1;
+						vw[i] = __vminu2(av[k], __byte_perm((uint32_t)wv[k * WS_WW], 0u, 0x1404));   // :359-360
+					}
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < WB; i++) {
+				const int rr = b0 + i;
+				if (rr <= NWALK) {
+					const int L4 = hw[i] & 0xffffu, R4 = hw[i] >> 16;
+					const char *pr = Pc + rr * (TWP * 4);
+					ph[i] = *reinterpret_cast<const float *>(pr + R4);
+					pl[i] = *reinterpret_cast<const float *>(pr - L4);
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < WB; i++) {
+				const int rr = b0 + i;
+				if (rr > NWALK) continue;
+				const int L4 = hw[i] & 0xffffu, R4 = hw[i] >> 16;
+				// run length L + R_ - 1 = (L4 + R4) / 4 as a float without a conversion: (2^23 + m) / 4 - 2^21, all exact
+				const float nf = fmaf(__int_as_float(0x4B000000 + L4 + R4), 0.25f, -2097152.0f);   // :368
+				float S = ph[i] - pl[i];                               // sum of the run (x - L, x + R_), :364-367
+				if (CENTER && VMODE != 2) S = fmaf(mu, nf, S);
+				if (VMODE == 2) {
+					run = ws_add2(run, ws_pack2(S, nf));
+					*reinterpret_cast<unsigned long long *>(rgb + (rr & (C::RING - 1)) * RROW) = run;
+				} else {
+					sn[rr] = ws_pack2(S, nf);
+				}
+				if (rr >= 2 * R + 1) {
+					const int k = rr - 2 * R - 1;                    // output row yb + k = relative row HALO + k = k + R + 1
+					const unsigned U8 = vw[i] & 0xffffu, D8 = vw[i] >> 16;   // U << 8, Dn << 8
+					float T, N;
+					if (VMODE == 2) {
+						constexpr int M = C::RING - 1, RMASK = C::RING * RROW - 1;
+						const int rk = HALO + k;
+						// rows y - U + 1 .. y + Dn - 1 (:361): run(rk + Dn - 1) - run(rk - U); the ring index wraps only
+						// where the (compile-time) row position says it can.  U8 * 8 = U * RROW.
+						int oh = D8 * 8 + (((rk - 1) & M) * RROW);
+						if (((rk - 1) & M) + R + 1 > M) oh &= RMASK;
+						int ol = ((rk & M) * RROW) - U8 * 8;
+						if ((rk & M) - R - 1 < 0) ol = (ol + C::RING * RROW) & RMASK;
+						const float2 a = *reinterpret_cast<const float2 *>(rgb + oh), b = *reinterpret_cast<const float2 *>(rgb + ol);
+						T = a.x - b.x;
+						N = a.y - b.y;
+					} else {
+						// ascending rows like the reference
+						unsigned long long acc = ws_pack2(0.0f, 0.0f);
+						{
+							// arm lengths as floats without a conversion: (2^23 + 256 a) / 256 - 2^15
+							const float Uf = fmaf(__int_as_float(0x4B000000 + U8), 0.00390625f, -32768.0f);
+							const float Df = fmaf(__int_as_float(0x4B000000 + D8), 0.00390625f, -32768.0f);
+#pragma unroll
+							for (int j = R; j >= 1; j--) {
+								const float m = __saturatef(Uf - (float)j);   // 1 iff U > j
+								acc = ws_fma2(sn[k + R + 1 - j], ws_pack2(m, m), acc);
+							}
+							acc = ws_add2(acc, sn[k + R + 1]);
+#pragma unroll
+							for (int j = 1; j <= R; j++) {
+								const float m = __saturatef(Df - (float)j);   // 1 iff Dn > j
+								acc = ws_fma2(sn[k + R + 1 + j], ws_pack2(m, m), acc);
+							}
+						}
+						ws_unpack2(acc, T, N);
+					}
+					float rc;
+					asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(N));   // count >= 1
+					float q = T * rc;
+					q = fmaf(fmaf(-q, N, T), rc, q);                     // one Newton step: T / N to the last bit or so (:373)
+					if (CENTER && VMODE == 2) q += mu;
+					asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(po), "f"(q), "r"(k), "r"(nst)
+						     : "memory");
+					po += ldb;
+				}
+			}
+		}
+		if (!valid_col && nv > 0) {                        // x + d*direction outside the image: plain copy, keeps NaN (:353-354)
+			const long idx0 = ((long)d * H + yb) * ld + x;
+			for (int k = 0; k < nv; k++) out[idx0 + (long)k * ld] = __ldg(vol + idx0 + (long)k * ld);
+		}
+		// the walkers only READ the stage: the mbarrier release / acquire orders those reads before the refill (the
+		// proxy fence is needed after generic WRITES, i.e. in the prefix warps; here it would also wait for the
+		// thread's global stores to drain, once per plane)
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&bar_empty[s]);
+	}
+	for (int dd = nproc; dd < dn; dd++) {                  // tiles entirely inside the invalid triangle: plain copy
+		const int d = d0 + dd;
+#pragma unroll 4
+		for (int k = 0; k < WS_HO; k++) {
+			const int y = yb + k;
+			const long idx = ((long)d * H + y) * ld + x;
+			if (y < H && x < W) out[idx] = __ldg(vol + idx);
+		}
+	}
+}
+
+template <int R, int WB, bool CENTER, int VMODE, int NPW>
+int launch_ws(const CUtensorMap &tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
+	      cudaStream_t s)
+{
+	using C = WSCfg<R>;
+	constexpr int smem = VMODE == 2 ? C::SMEM_RING : C::SMEM_NORING;
+	static bool attr_done[64] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!attr_done[dev & 63]) {
+		ADC_CUDA(cudaFuncSetAttribute(cbca_ws_kernel<R, WB, CENTER, VMODE, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		attr_done[dev & 63] = true;
+	}
+	static const int dch_env = getenv("ADCENSUS_CBCA_DCH") ? atoi(getenv("ADCENSUS_CBCA_DCH")) : 0;   // tuning knob, not part of the ABI
+	int dch = dch_env > 0 ? dch_env : WS_DCH;
+	if (dch > WS_DCH) dch = WS_DCH;
+	dch = adc_div_up(D, adc_div_up(D, dch));               // equal chunks (19 x 12 at D = 228)
+	const long HW = (long)H * W;
+	dim3 grid(adc_div_up(W, WS_TX), adc_div_up(H, WS_TY), adc_div_up(D, dch));
+	cbca_ws_kernel<R, WB, CENTER, VMODE, NPW><<<grid, ws_nt(NPW), smem, s>>>(tm, hv, hv + 2 * HW, hv + HW, hv + 3 * HW, vol, out, D, H, W, ld, direction, dch);
+	ADC_CHECK_LAUNCH();
+	return 0;
+}
+
+}  // namespace
+
+// ---- internal entry points (cbca_tma.cu dispatches here for short arms) ------------------------------
+int adc_cbca_ws_max_halo() { return 4; }
+
+void adc_cbca_ws_box(int halo, int *box_w, int *box_h)
+{
+	*box_w = WS_TWP;
+	*box_h = halo <= 1 ? WSCfg<1>::TH : WSCfg<4>::TH;
+}
+
+// hv: packed arms (adc_pack_arms_hv); tm: tensor map of `vol` with the box of adc_cbca_ws_box(halo)
+int adc_cbca_ws(const CUtensorMap *tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
+		int halo, cudaStream_t s)
+{
+	// Tuning knobs (environment, read once; not part of the ABI).  Defaults = the fastest measured on B200 at the bench size
+	// that also keeps the disparity map inside the 1e-4-of-the-pixels bar: running sums in the ring, centred (VMODE 2,
+	// CENTER 1: 0.38 ms / iteration, 1.5e-5 of the pixels differ); VMODE 1 sums every row range tap by tap (0.39 ms, 9e-6).
+	static const int center = getenv("ADCENSUS_CBCA_CENTER") ? atoi(getenv("ADCENSUS_CBCA_CENTER")) : 1;
+	static const int vmode = getenv("ADCENSUS_CBCA_VMODE") ? atoi(getenv("ADCENSUS_CBCA_VMODE")) : 2;
+	static const int npw = getenv("ADCENSUS_CBCA_NPW") ? atoi(getenv("ADCENSUS_CBCA_NPW")) : 4;
+#define WS_GO(R_, WB_, C_, V_, N_) return launch_ws<R_, WB_, C_, V_, N_>(*tm, hv, vol, out, D, H, W, ld, direction, s)
+	if (halo <= 1) {
+		if (vmode == 2) { if (center) WS_GO(1, 6, true, 2, 4); else WS_GO(1, 6, false, 2, 4); }
+		if (center) WS_GO(1, 6, true, 1, 4); else WS_GO(1, 6, false, 1, 4);
+	}
+	if (halo <= 4) {
+		if (npw == 6) {
+			if (vmode == 2) { if (center) WS_GO(4, 4, true, 2, 6); else WS_GO(4, 4, false, 2, 6); }
+			if (center) WS_GO(4, 4, true, 1, 6); else WS_GO(4, 4, false, 1, 6);
+		}
+		if (vmode == 2) { if (center) WS_GO(4, 4, true, 2, 4); else WS_GO(4, 4, false, 2, 4); }
+		if (center) WS_GO(4, 4, true, 1, 4); else WS_GO(4, 4, false, 1, 4);
+	}
+#undef WS_GO
+	return ADCENSUS_ELIMIT;
+}

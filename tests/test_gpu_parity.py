@@ -467,10 +467,22 @@ def test_full_size_default_mode_against_live_reference(H, W, C, D, preset, over)
     sp.close()
 
 
+def _mb_inputs(H, W, C):
+    g = torch.Generator(device=dev()).manual_seed(3)
+    fL = torch.nn.functional.normalize(torch.randn((C, H, W), device=dev(), generator=g), dim=0)
+    fR = torch.nn.functional.normalize(torch.randn((C, H, W), device=dev(), generator=g), dim=0)
+    rng = np.random.default_rng(3)
+    img = synth.natural_image(rng, H, W + 16)
+    st = lambda x: cu(((x - x.mean()) / x.std(ddof=1)).astype(np.float32))
+    return fL, fR, st(img[:, 16:]).contiguous(), st(img[:, :W]).contiguous()
+
+
 def test_middlebury_size_against_live_reference():
-    """BASELINE.json config 5's volume on ONE GPU (the scaling denominator of the row-band split): 2000 x 3000, d = 400,
-    'mb fast' preset (main.lua:281-293: no CBCA, no LR check, direction -1 only), exact pipeline against the reference's
-    kernels: left.bin and disp.bin bit for bit."""
+    """BASELINE.json config 5 ('mb fast', main.lua:281-293: no CBCA, no LR check, direction -1 only) on ONE GPU against the
+    reference's kernels, left.bin and disp.bin bit for bit, at the LARGEST height the reference can address: its kernels
+    index the volume with `int` (adcensus.cu:1472 `d * size23 + id`, :560 etc.), so 2000 x 3000 x 400 = 2.4e9 elements
+    overflows in the reference itself (measured: 2.16e9 elements of its left.bin are garbage there).  1776 x 3000 x 400 =
+    2.13e9 < 2^31 is the same workload per row; the full 2000 rows are covered by the test below."""
     from oracle import refdriver
 
     if not os.path.exists(refdriver.REF_LIB):
@@ -478,15 +490,9 @@ def test_middlebury_size_against_live_reference():
     free, _ = torch.cuda.mem_get_info()
     if free < 120e9:
         pytest.skip("needs ~110 GB of device memory")
-    H, W, C, D = 2000, 3000, 64, 400
+    H, W, C, D = 1776, 3000, 64, 400
     opt = pipeline.make_params("mb", "fast")
-    g = torch.Generator(device=dev()).manual_seed(3)
-    fL = torch.nn.functional.normalize(torch.randn((C, H, W), device=dev(), generator=g), dim=0)
-    fR = torch.nn.functional.normalize(torch.randn((C, H, W), device=dev(), generator=g), dim=0)
-    rng = np.random.default_rng(3)
-    img = synth.natural_image(rng, H, W + 16)
-    st = lambda x: cu(((x - x.mean()) / x.std(ddof=1)).astype(np.float32))
-    iL, iR = st(img[:, 16:]).contiguous(), st(img[:, :W]).contiguous()
+    fL, fR, iL, iR = _mb_inputs(H, W, C)
     sp = pipeline.StereoPipeline(C, D, H, W, opt, cbca_mode="exact")
     volL = torch.empty((D, H, W), device=dev())
     disp = sp.run(fL, fR, iL, iR, volL=volL)
@@ -498,6 +504,27 @@ def test_middlebury_size_against_live_reference():
     for got, ref, what in ((volL, wL[0], "left.bin"), (disp, want[0, 0], "disp.bin")):
         bad = ~((got == ref) | (torch.isnan(got) & torch.isnan(ref)))
         assert int(bad.sum()) == 0, "%s: %d elements differ from the reference at Middlebury size" % (what, int(bad.sum()))
+
+
+def test_middlebury_full_size_64bit_indexing():
+    """2000 x 3000 x 400 (2.4e9 elements, beyond `int`): the fused pipeline against the operator chain (adcensus.* one by
+    one, different kernels for the transposes / SGM layout / arg-min) -- equal bit for bit."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 140e9:
+        pytest.skip("needs ~130 GB of device memory")
+    H, W, C, D = 2000, 3000, 64, 400
+    opt = pipeline.make_params("mb", "fast")
+    fL, fR, iL, iR = _mb_inputs(H, W, C)
+    sp = pipeline.StereoPipeline(C, D, H, W, opt, cbca_mode="exact")
+    volL = torch.empty((D, H, W), device=dev())
+    disp = sp.run(fL, fR, iL, iR, volL=volL)
+    torch.cuda.synchronize()
+    sp.close()
+    want, wL, _ = pipeline.stereo_predict(torch.stack([iL, iR])[:, None], torch.stack([fL, fR]), opt, D, want_vols=True)
+    torch.cuda.synchronize()
+    for got, ref, what in ((volL, wL.reshape(D, H, W), "left volume"), (disp, want.reshape(H, W), "disparity map")):
+        bad = ~((got == ref) | (torch.isnan(got) & torch.isnan(ref)))
+        assert int(bad.sum()) == 0, "%s: %d elements differ between the fused pipeline and the operator chain" % (what, int(bad.sum()))
 
 
 FULL_SIZE = [
