@@ -269,6 +269,23 @@ int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const float *const *
 				  const float *const *featR_host, const float *const *imgL_host,
 				  const float *const *imgR_host, float *const *disp_host);
 
+/* ---- the accurate ('slow') architecture's scorer head (csrc/scorer_head.cu) -------------------------------------
+ * Replaces the per-disparity loop of main.lua:958-984 over net_te2 (main.lua:688-695: l2 x [SpatialConvolution1_fw,
+ * ReLU], SpatialConvolution1_fw(nh2 -> 1), Sigmoid; SpatialConvolution1_fw.lua:11-31 = addmm + bias per pixel) by one
+ * fused tcgen05 kernel.  Outside libadcensus.so in the reference (a Lua nn module chain), hence a mccnn_* entry.
+ * W[i] (out_i x in_i, row-major) and b[i] (out_i), i = 0 .. l2, DEVICE pointers in net_te2's order: layer 0 is
+ * (nh2 x 2 fm), layers 1 .. l2-1 (nh2 x nh2), layer l2 (1 x nh2).  Limits: l2 <= 4, nh2 a multiple of 128 and <= 384,
+ * fm a multiple of 8 with 2 fm <= 384 (the kitti / kitti2015 / mb nets: fm 112, nh2 384, l2 3..4). */
+typedef struct mccnn_scorer_head mccnn_scorer_head;
+int mccnn_scorer_head_create(mccnn_scorer_head **out, int fm, int nh2, int l2, const float *const *W, const float *const *b,
+			     int device, adcensus_stream_t stream);
+void mccnn_scorer_head_destroy(mccnn_scorer_head *h);
+/* featL / featR: (fm, H, W) tower outputs; volL / volR: (D, H, W), either may be NULL.  Writes volL[d, y, x] for x >= d and
+ * volR[d, y, x - d] (the same score, main.lua:976); all other entries keep the caller's NaN fill (:962); fix_border (:981)
+ * is the caller's next call.  nterms 3: bf16-split operands, fp32-grade (1e-4 contract); 1: plain bf16. */
+int mccnn_scorer_head_forward(const mccnn_scorer_head *h, const float *featL, const float *featR, float *volL, float *volR,
+			      int H, int W, int D, int nterms, adcensus_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,3 +58,20 @@ def test_first_layer_splits_into_a_left_and_a_right_half():
     rest = sh.head_pixels(h1.astype(np.float32), [(np.eye(nh2, dtype=np.float32), np.zeros(nh2, np.float32))] + layers[1:])
     want = sh.head_volume(fL, fR, d + 1, layers, -1)[d, :, d:].ravel()
     assert np.abs(rest - want).max() < 1e-5
+
+
+def test_against_the_pytorch_restatement_fixture():
+    """tests/golden/scorer_head.npz: main.lua:962-978 + SpatialConvolution1_fw.lua:11-31 restated in PyTorch (CPU fp32:
+    addmm, bias add, relu, sigmoid), generator oracle/make_scorer_head_golden.py.  The float64-accumulating oracle agrees
+    with it to fp32 rounding of a 384-term product chain."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "scorer_head.npz"))
+    layers = [(g["w%d" % i], g["b%d" % i]) for i in range(5)]
+    D = int(g["D"])
+    for direction, key in ((-1, "volL"), (1, "volR")):
+        got = sh.head_volume(g["featL"], g["featR"], D, layers, direction)
+        want = g[key][0]
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        m = ~np.isnan(want)
+        assert np.abs(got[m] - want[m]).max() < 2e-6
