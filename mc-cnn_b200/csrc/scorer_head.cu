@@ -23,8 +23,9 @@
 //     slot); they are L2-resident (2.1 MB for kitti) and shared by all CTAs;
 //   * layer 1 takes its rows straight from the (fm, H, W) tower outputs (left pixel x, right pixel x - d: coalesced loads
 //     along x), the last hidden layer's epilogue folds the nh2 -> 1 product, bias and sigmoid and stores the two volumes.
-// A CTA owns (image row, 128-pixel tile) and loops over the disparities.  Roles: warps 0-3 build / read the tile, warp 4
-// streams weights, warp 5 allocates TMEM and issues the MMAs.
+// A CTA owns (image row, 128-pixel tile) and loops over the disparities.  Roles: warps 0-7 build / read the tile (two
+// threads per row, one per column half; warp w may touch the TMEM lanes of quadrant w % 4), warp 8 streams weights,
+// warp 9 allocates TMEM and issues the MMAs.
 //
 // Roofline: tensor-bound.  Per valid (pixel, d): 2 * (2 fm * nh2 + (l2 - 1) * nh2^2) flop = 1.06 MFLOP for kitti
 // (fm 112, nh2 384, l2 4), x 3 for the split.
@@ -41,7 +42,8 @@ constexpr int SH_NMAX = 384, SH_KMAX = 384, SH_LMAX = 4;
 constexpr int SH_SLAB = 2 * SH_NMAX * 16;    // ring slot: one K = 16 step of B, [2 chunks][N][8 bf16]
 constexpr int SH_ACHUNK = SH_M * 16;         // one 8-wide K chunk of A: [128 rows][8 bf16]
 constexpr int SH_ABYTES = (SH_KMAX / 8) * SH_ACHUNK;
-constexpr int SH_NT = 192;
+constexpr int SH_NFEED = 256;                // tile builders / epilogue: 2 threads per row (column halves)
+constexpr int SH_NT = SH_NFEED + 64;         // + weight producer warp + MMA warp
 constexpr unsigned SH_SPIN_LIMIT = 1u << 28; // a wait that long is a protocol bug: trap instead of hanging the GPU
 
 template <int NTERMS>
@@ -54,7 +56,8 @@ struct SHCfg {
 	static constexpr int NCONST = SH_LMAX * SH_NMAX + SH_NMAX + 4;
 	static constexpr int OFF_BAR = OFF_CONST + NCONST * 4;                   // full[NSLOT], empty[NSLOT], a_ready, acc_full
 	static constexpr int OFF_TPTR = OFF_BAR + (2 * NSLOT + 2) * 8;
-	static constexpr int SMEM = OFF_TPTR + 16;
+	static constexpr int OFF_PART = OFF_TPTR + 16;                           // [128] partial dot products of column half 1
+	static constexpr int SMEM = OFF_PART + SH_M * 4;
 	static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -104,6 +107,7 @@ __device__ __forceinline__ void sh_commit(uint64_t *bar)
 }
 __device__ __forceinline__ void sh_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void sh_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// 32 accumulator columns of this thread's row -> registers (asynchronous: sh_tmem_wait before the first use)
 __device__ __forceinline__ void sh_tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -115,7 +119,17 @@ __device__ __forceinline__ void sh_tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 		       "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
 		     : "r"(taddr)
 		     : "memory");
-	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// wait for the outstanding tcgen05.ld; the registers are operands so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void sh_tmem_wait(uint32_t (&r)[32])
+{
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+		     : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+		       "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+		       "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+		       "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+		     :
+		     : "memory");
 }
 __device__ __forceinline__ void sh_bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
@@ -173,6 +187,7 @@ scorer_head_kernel(const SHParams p)
 	uint64_t *bar_a = bar_empty + NSLOT;       // the A operand of the next layer is in shared memory
 	uint64_t *bar_acc = bar_a + 1;             // the accumulator of the current layer is complete
 	uint32_t *tptr = reinterpret_cast<uint32_t *>(sh_smem + C::OFF_TPTR);
+	float *part = reinterpret_cast<float *>(sh_smem + C::OFF_PART);
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int x0 = blockIdx.x * SH_M, y = blockIdx.y;
@@ -188,12 +203,12 @@ scorer_head_kernel(const SHParams p)
 			mbar_init(&bar_full[s], 1);
 			mbar_init(&bar_empty[s], 1);
 		}
-		mbar_init(bar_a, SH_M);
+		mbar_init(bar_a, SH_NFEED);
 		mbar_init(bar_acc, 1);
 		mbar_fence_init();
 	}
 	for (int i = tid; i < C::NCONST; i += SH_NT) cst[i] = p.consts[i];
-	if (warp == 5) {                               // TMEM: 512 columns (the accumulator needs N <= 384)
+	if (warp == 9) {                               // TMEM: 512 columns (the accumulator needs N <= 384)
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma_smem_addr(tptr)), "r"(512) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
@@ -202,7 +217,7 @@ scorer_head_kernel(const SHParams p)
 	sh_fence_after();
 	const uint32_t tbase = *tptr;
 
-	if (warp == 4) {
+	if (warp == 8) {
 		// ------------------------------------------------------------ weight producer
 		if (lane == 0) {
 			unsigned it = 0;
@@ -218,7 +233,7 @@ scorer_head_kernel(const SHParams p)
 						}
 				}
 		}
-	} else if (warp == 5) {
+	} else if (warp == 9) {
 		// ------------------------------------------------------------ MMA issuer
 		if (lane == 0) {
 			const uint32_t a_hi_s = tma_smem_addr(a_hi), a_lo_s = tma_smem_addr(a_lo), ring_s = tma_smem_addr(ring);
@@ -264,11 +279,14 @@ scorer_head_kernel(const SHParams p)
 				}
 		}
 	} else {
-		// ------------------------------------------------------------ tile builders / epilogue (thread = row = TMEM lane)
-		const int m = tid;
+		// ------------------------------------------------------------ tile builders / epilogue
+		// thread = (row m = TMEM lane, column half hf): warp w covers lanes 32 (w % 4) .. + 31, half w / 4
+		const int m = (warp & 3) * 32 + lane, hf = warp >> 2;
 		const int x = x0 + m;
 		const int fm = p.fm, nc1 = 2 * fm / 8, ncl = fm / 8;
-		const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
+		const int kc_a = hf ? (nc1 + 1) / 2 : 0, kc_b = hf ? nc1 : (nc1 + 1) / 2;     // layer-1 K chunks of this half
+		const int cn = N / 2, ca = hf * cn;                                            // accumulator columns of this half
+		const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16);
 		const float *w5 = cst + SH_LMAX * SH_NMAX;
 		const float b5 = w5[SH_NMAX];
 		unsigned use = 0;
@@ -278,18 +296,18 @@ scorer_head_kernel(const SHParams p)
 			{
 				const float *pl = p.featL + (long)y * W + (rowok ? x : 0);
 				const float *pr = p.featR + (long)y * W + (rowok ? x - d : 0);
-				for (int kc0 = 0; kc0 < nc1; kc0 += 4) {
+				for (int kc0 = kc_a; kc0 < kc_b; kc0 += 4) {
 					float v[4][8];
 #pragma unroll
 					for (int u = 0; u < 4; u++) {
 						const int kc = kc0 + u;
 						const float *src = kc < ncl ? pl + (long)(8 * kc) * HW : pr + (long)(8 * (kc - ncl)) * HW;
 #pragma unroll
-						for (int e = 0; e < 8; e++) v[u][e] = (rowok && kc < nc1) ? __ldg(src + (long)e * HW) : 0.0f;
+						for (int e = 0; e < 8; e++) v[u][e] = (rowok && kc < kc_b) ? __ldg(src + (long)e * HW) : 0.0f;
 					}
 #pragma unroll
 					for (int u = 0; u < 4; u++)
-						if (kc0 + u < nc1) sh_store8<NTERMS>(a_hi, a_lo, kc0 + u, m, v[u]);
+						if (kc0 + u < kc_b) sh_store8<NTERMS>(a_hi, a_lo, kc0 + u, m, v[u]);
 				}
 			}
 			fence_proxy_async_smem();              // generic stores -> visible to the tensor core's (async proxy) reads
@@ -299,17 +317,32 @@ scorer_head_kernel(const SHParams p)
 				sh_wait(bar_acc, use & 1);
 				sh_fence_after();
 				const float *bias = cst + l * SH_NMAX;
+				// 32 columns at a time, the next 32 already in flight while these are processed
+				uint32_t ra[32], rb[32];
+				sh_tmem_ld32(trow + ca, ra);
 				if (l + 1 < L) {
 					// hidden layer: + bias, ReLU (SpatialConvolution1_fw.lua:21-27, cudnn.ReLU), next layer's operand
-					for (int c0 = 0; c0 < N; c0 += 32) {
-						uint32_t r[32];
-						sh_tmem_ld32(trow + c0, r);
+					for (int c0 = ca; c0 < ca + cn; c0 += 64) {
+						sh_tmem_wait(ra);
+						if (c0 + 32 < ca + cn) sh_tmem_ld32(trow + c0 + 32, rb);
 #pragma unroll
 						for (int g = 0; g < 4; g++) {
 							float v[8];
 #pragma unroll
-							for (int e = 0; e < 8; e++) v[e] = fmaxf(__uint_as_float(r[8 * g + e]) + bias[c0 + 8 * g + e], 0.0f);
+							for (int e = 0; e < 8; e++) v[e] = fmaxf(__uint_as_float(ra[8 * g + e]) + bias[c0 + 8 * g + e], 0.0f);
 							sh_store8<NTERMS>(a_hi, a_lo, c0 / 8 + g, m, v);
+						}
+						if (c0 + 32 < ca + cn) {
+							sh_tmem_wait(rb);
+							if (c0 + 64 < ca + cn) sh_tmem_ld32(trow + c0 + 64, ra);
+#pragma unroll
+							for (int g = 0; g < 4; g++) {
+								float v[8];
+#pragma unroll
+								for (int e = 0; e < 8; e++)
+									v[e] = fmaxf(__uint_as_float(rb[8 * g + e]) + bias[c0 + 32 + 8 * g + e], 0.0f);
+								sh_store8<NTERMS>(a_hi, a_lo, (c0 + 32) / 8 + g, m, v);
+							}
 						}
 					}
 					fence_proxy_async_smem();
@@ -318,28 +351,40 @@ scorer_head_kernel(const SHParams p)
 				} else {
 					// last hidden layer folded with the nh2 -> 1 layer and the sigmoid (main.lua:693-694)
 					float acc = 0.0f;
-					for (int c0 = 0; c0 < N; c0 += 32) {
-						uint32_t r[32];
-						sh_tmem_ld32(trow + c0, r);
+					for (int c0 = ca; c0 < ca + cn; c0 += 64) {
+						sh_tmem_wait(ra);
+						if (c0 + 32 < ca + cn) sh_tmem_ld32(trow + c0 + 32, rb);
 #pragma unroll
 						for (int e = 0; e < 32; e++)
-							acc = fmaf(fmaxf(__uint_as_float(r[e]) + bias[c0 + e], 0.0f), w5[c0 + e], acc);
+							acc = fmaf(fmaxf(__uint_as_float(ra[e]) + bias[c0 + e], 0.0f), w5[c0 + e], acc);
+						if (c0 + 32 < ca + cn) {
+							sh_tmem_wait(rb);
+							if (c0 + 64 < ca + cn) sh_tmem_ld32(trow + c0 + 64, ra);
+#pragma unroll
+							for (int e = 0; e < 32; e++)
+								acc = fmaf(fmaxf(__uint_as_float(rb[e]) + bias[c0 + 32 + e], 0.0f), w5[c0 + 32 + e], acc);
+						}
 					}
 					sh_fence_before();             // the accumulator has been read: the next tile's MMAs may overwrite it
-					const float z = acc + b5;
-					const float s = 1.0f / (1.0f + expf(-z));
-					if (rowok) {
-						const long o = ((long)d * p.H + y) * W;
-						if (p.volL) p.volL[o + x] = s;           // main.lua:976, direction -1: columns d ..
-						if (p.volR) p.volR[o + x - d] = s;       //                direction +1: columns .. W - d
+					if (hf) part[m] = acc;
+					asm volatile("bar.sync 1, %0;" ::"n"(SH_NFEED) : "memory");
+					if (!hf) {
+						const float z = (acc + part[m]) + b5;
+						const float s = 1.0f / (1.0f + expf(-z));
+						if (rowok) {
+							const long o = ((long)d * p.H + y) * W;
+							if (p.volL) p.volL[o + x] = s;           // main.lua:976, direction -1: columns d ..
+							if (p.volR) p.volR[o + x - d] = s;       //                direction +1: columns .. W - d
+						}
 					}
+					asm volatile("bar.sync 1, %0;" ::"n"(SH_NFEED) : "memory");   // part[] free for the next tile
 				}
 			}
 		}
 	}
 	sh_fence_before();
 	__syncthreads();
-	if (warp == 5) {
+	if (warp == 9) {
 		sh_fence_after();
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512) : "memory");
 	}
