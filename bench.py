@@ -322,6 +322,110 @@ def load_traffic(workload):
     return {}, None
 
 
+def rowband_block(rank, world, local):
+    """One stereo pair split by row bands over the N ranks (BASELINE config 5 at N = 8, the bench pair
+    otherwise): CUDA-event time (barrier on both sides, max over ranks), the single-GPU fused pipeline on the same inputs
+    (rank 0) and the number of disparity-map pixels that differ from it.  Appended to the bench line at N >= 2 so that the
+    driver's scaling run records it; never part of `value`."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mccnn_b200 import pipeline, rowband, synth
+
+    dev = torch.device("cuda", local)
+    if world >= 8:
+        H, W, D, C, preset, name = 2000, 3000, 400, 64, ("mb", "fast"), "middlebury_2000x3000_d400_mb_fast"
+    else:
+        H, W, D, C, preset, name = 370, 1226, 228, 64, ("kitti", "accurate_cbca4"), "kitti_accurate_370x1226_d228_cbca4_sgm4"
+    res = {"workload": name, "n_gpus": world, "split": "row bands; halo rows before the CBCA blocks, vertical SGM passes as a "
+           "wavefront over column chunks carrying the W x D line state (NCCL send/recv)"}
+    try:
+        opt = pipeline.make_params(*preset)
+        g = torch.Generator(device=dev).manual_seed(7)
+        featL = torch.nn.functional.normalize(torch.randn((C, H, W), device=dev, generator=g), dim=0)
+        featR = torch.nn.functional.normalize(torch.randn((C, H, W), device=dev, generator=g), dim=0)
+        img = synth.natural_image(np.random.default_rng(7), H, W + 16)
+        st = lambda x: torch.from_numpy(((x - x.mean()) / x.std(ddof=1)).astype(np.float32)).to(dev)
+        imgL, imgR = st(img[:, 16:]).contiguous(), st(img[:, :W]).contiguous()
+        ops, comm = rowband.CudaOps(dev), rowband.Comm()
+        out = rowband.stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm)
+        times = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier_sync(world)
+            e0.record()
+            out = rowband.stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm)
+            e1.record()
+            barrier_sync(world)
+            times.append(max_over_ranks(e0.elapsed_time(e1), world))
+        res["ms"] = round(min(times), 3)
+        if rank == 0:
+            sp = pipeline.StereoPipeline(C, D, H, W, opt, device=local, cbca_mode="exact")   # the band driver runs the exact operators
+            ref = sp.run(featL, featR, imgL, imgR)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ref = sp.run(featL, featR, imgL, imgR)
+            e1.record()
+            torch.cuda.synchronize()
+            res["single_gpu_ms"] = round(e0.elapsed_time(e1), 3)
+            res["speedup"] = round(res["single_gpu_ms"] / res["ms"], 3)
+            res["efficiency"] = round(res["single_gpu_ms"] / res["ms"] / world, 3)
+            bad = ~((out == ref) | (torch.isnan(out) & torch.isnan(ref)))
+            res["mismatches_vs_single_gpu"] = int(bad.sum())
+            sp.close()
+    except Exception as e:  # the block must never take the bench line down
+        res["error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+    return res
+
+
+def scorer_head_block(local, peaks_path=None):
+    """The accurate architecture's scorer head (csrc/scorer_head.cu) at the bench size: ms per volume pair
+    and tensor-core TFLOP/s against the measured dense bf16 peak.  Reported beside the headline, never part of it."""
+    import numpy as np
+    import torch
+
+    from mccnn_b200 import scorer_head
+
+    dev = torch.device("cuda", local)
+    fm, nh2, l2, H, W, D = 112, 384, 4, 370, 1226, 228
+    g = torch.Generator(device=dev).manual_seed(0)
+    fL = torch.relu(torch.randn((fm, H, W), device=dev, generator=g))
+    fR = torch.relu(torch.randn((fm, H, W), device=dev, generator=g))
+    rng = np.random.default_rng(0)
+    layers, n_in = [], 2 * fm                                   # random-init net_te2 (no trained nets offline)
+    for _ in range(l2):
+        layers.append(((rng.standard_normal((nh2, n_in)) / np.sqrt(n_in)).astype(np.float32), (0.1 * rng.standard_normal(nh2)).astype(np.float32)))
+        n_in = nh2
+    layers.append(((rng.standard_normal((1, nh2)) / np.sqrt(nh2)).astype(np.float32), (0.1 * rng.standard_normal(1)).astype(np.float32)))
+    head = scorer_head.ScorerHead(layers, device=local)
+    rows = H * (D * W - D * (D - 1) // 2)
+    flop_row = 2 * (2 * fm * nh2 + (l2 - 1) * nh2 * nh2 + nh2)
+    peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    out = {"workload": "kitti slow net_te2 (fm 112, nh2 384, l2 4) at 370x1226 d=228, both volumes", "bound": "tensor"}
+    for nterms, key in ((3, "bf16_split_fp32_grade"), (1, "bf16_plain")):
+        head.volumes(fL, fR, D, nterms=nterms)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        head.volumes(fL, fR, D, nterms=nterms)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        ach = rows * flop_row * nterms / ms / 1e9
+        out[key] = {"ms": round(ms, 2), "useful_tflops": round(rows * flop_row / ms / 1e9, 1), "achieved": round(ach, 1), "unit": "TFLOP/s",
+                    "peak": peak, "frac": round(ach / peak, 4) if peak else None,
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peak else None}
+    head.close()
+    return out
+
+
 def run_b200(args):
     import torch
 
@@ -455,7 +559,18 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(cfg, opt)
+        if not args.small:
+            try:
+                out["scorer_head"] = scorer_head_block(local)
+            except Exception as e:
+                out["scorer_head"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     sp.close()
+    del dev_in
+    torch.cuda.empty_cache()
+    if world > 1 and not args.small:
+        rb = rowband_block(rank, world, local)
+        if out is not None:
+            out["rowband"] = rb
     if world > 1:
         import torch.distributed as dist
 
