@@ -24,6 +24,7 @@
 // Roofline: 2*C*H*W*4 bytes read + 2*valid*4 bytes written (valid = H*(D*W -
 // D(D-1)/2)); at C=64 the FMA work (2*C flop per output) sits at the fp32 ridge
 // of the chip, so the kernel is tuned like a GEMM and reported against HBM.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -52,6 +53,13 @@ __device__ __forceinline__ unsigned long long sj_fma2(unsigned long long a, unsi
 	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
 	return d;
 }
+
+}  // namespace
+// second generation (stereo_join_tma.cu): TMA-staged feature rows
+int adc_stereo_join_tma_ok(const float *input_L, const float *input_R, const float *output_L, const float *output_R, int H, int W);
+int adc_stereo_join_tma(const float *input_L, const float *input_R, float *output_L, float *output_R,
+			int C, int D, int H, int W, int ldo, int ns, cudaStream_t s);
+namespace {
 
 template <int NS>
 struct SJCfg {
@@ -341,6 +349,9 @@ int adc_stereo_join(const float *input_L, const float *input_R, float *output_L,
 	if (C < 1 || D < 1 || H < 1 || W < 1 || H > 65535 || ldo < W) return ADCENSUS_EINVAL;
 	if (C > 128) return ADCENSUS_ELIMIT;  // reference: float L_cache[128] (adcensus.cu:1460-1461)
 	const int ns = sj_ns(D);
+	static const int use_tma = getenv("ADCENSUS_SJ_TMA") ? atoi(getenv("ADCENSUS_SJ_TMA")) : 1;   // tuning knob
+	if (use_tma && !fast && adc_stereo_join_tma_ok(input_L, input_R, output_L, output_R, H, W) && (ldo % 4 == 0 || ldo == W))
+		return adc_stereo_join_tma(input_L, input_R, output_L, output_R, C, D, H, W, ldo, ns, s);
 	if (fast && adc_stereo_join_fast_ok(input_L, input_R, output_L, output_R, W, ldo)) {
 		CUtensorMap local;
 		if (!tmL) {
