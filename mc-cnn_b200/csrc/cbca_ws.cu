@@ -30,30 +30,35 @@
 
 namespace {
 
-constexpr int WS_TX = 128, WS_TY = 64, WS_HO = 32;
-constexpr int WS_NWT = 256;                 // walker threads (8 warps)
-__host__ __device__ constexpr int ws_nt(int npw) { return WS_NWT + 32 * npw + 32; }   // walkers + prefix warps + one producer warp
+constexpr int WS_TX = 128, WS_TY = 64;
+__host__ __device__ constexpr int ws_nwt(int ho) { return WS_TX * (WS_TY / ho); }                  // walker threads: column x row group
+// walkers + prefix warps + one producer warp; the 512-walker form has no producer warp (prefix warp 0 issues the TMA) so that the
+// block stays within 640 threads = 96 registers per thread
+__host__ __device__ constexpr int ws_nt(int npw, int ho) { return ws_nwt(ho) + 32 * npw + (ho < 32 ? 0 : 32); }
 constexpr int WS_DCH = 20;                  // max disparities per CTA
 constexpr int WS_WW = WS_TX + WS_DCH;       // pitch of the right-image arm windows
 constexpr int WS_NST = 3;                   // tile stages
 constexpr int WS_TWP = 144;                 // tile pitch = TMA box width: 16 lanes x 9 columns, = 16 (mod 32)
 
-template <int R>
+template <int R, int HO>
 struct WSCfg {
 	static constexpr int HALO = R + 1;                 // the prefix differences index the first EXCLUDED pixel
 	static constexpr int HX = (HALO + 3) & ~3;         // left halo in columns (TMA: 16-byte aligned start along x)
 	static constexpr int TH = WS_TY + 2 * R + 1;       // image rows y0 - HALO .. y0 + TY + R - 1
-	static constexpr int NWALK = 2 * R + WS_HO;        // rows a thread walks for its 32 outputs
+	static constexpr int NWALK = 2 * R + HO;           // rows a thread walks for its HO outputs
+	static constexpr int NWT = ws_nwt(HO);
+	static constexpr bool H16 = HO < 32;               // narrow the H-word window to 16 bits (shared-memory budget of the 512-thread form)
 	static constexpr int TILE_BYTES = TH * WS_TWP * 4; // bytes one TMA box delivers
 	static constexpr int STAGE_BYTES = (TILE_BYTES + 127) & ~127;
 	static constexpr int OFF_WINH = WS_NST * STAGE_BYTES;
-	static constexpr int OFF_WINV = OFF_WINH + TH * WS_WW * 4;
+	static constexpr int OFF_WINV = OFF_WINH + ((TH * WS_WW * (H16 ? 2 : 4) + 15) & ~15);
 	static constexpr int OFF_MU = OFF_WINV + ((WS_TY * WS_WW * 2 + 15) & ~15);
 	static constexpr int OFF_BAR = OFF_MU + 16;
-	static constexpr int OFF_RING = OFF_BAR + ((3 * WS_NST * 8 + 15) & ~15);   // VMODE 2 only: [16][WS_NWT] (T, N) per thread
-	static constexpr int RING = 16;
+	static constexpr int OFF_RING = OFF_BAR + ((3 * WS_NST * 8 + 15) & ~15);   // VMODE 2 only: [RING][NWT] (T, N) per thread
+	static constexpr int RING = HO < 32 ? 2 * R + 2 : 16;   // a power of two where the budget allows (cheaper wrap)
 	static constexpr int SMEM_NORING = OFF_RING;
-	static constexpr int SMEM_RING = OFF_RING + RING * WS_NWT * 8;
+	static constexpr int SMEM_RING = OFF_RING + RING * NWT * 8;
+	static_assert(SMEM_RING <= 232448, "shared memory budget");
 	static_assert(RING >= 2 * R + 2, "ring too small");
 	static_assert(HX + WS_TX + R <= WS_TWP, "tile pitch too small");
 	static_assert(TH <= 256, "TMA box limit");
@@ -93,19 +98,20 @@ __device__ __forceinline__ unsigned long long ws_add2(unsigned long long a, unsi
 //   2  running (T, N) down the column in a per-thread shared-memory ring, output = difference of two entries (fewest
 //      instructions, most shared-memory traffic); with CENTER the running sums carry deviations only
 // (predicated add.rn.f32x2 was tried first: ptxas turns each into FADD2 + 2 SEL, 70 instructions per output)
-template <int R, int WB, bool CENTER, int VMODE, int WS_NPW>
-__global__ void __launch_bounds__(ws_nt(WS_NPW), 1)
+template <int R, int WB, bool CENTER, int VMODE, int WS_NPW, int WS_HO>
+__global__ void __launch_bounds__(ws_nt(WS_NPW, WS_HO), 1)
 cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 	       const uint32_t *__restrict__ a0h, const uint32_t *__restrict__ a0v,
 	       const uint32_t *__restrict__ a1h, const uint32_t *__restrict__ a1v,
 	       const float *__restrict__ vol, float *__restrict__ out,
 	       int D, int H, int W, int ld, int direction, int dch)
 {
-	using C = WSCfg<R>;
-	constexpr int WS_NT = ws_nt(WS_NPW);
+	using C = WSCfg<R, WS_HO>;
+	constexpr int WS_NT = ws_nt(WS_NPW, WS_HO), WS_NWT = C::NWT;
 	constexpr int HALO = C::HALO, HX = C::HX, TH = C::TH, NWALK = C::NWALK, TWP = WS_TWP;
 	extern __shared__ __align__(128) unsigned char ws_smem[];
-	uint32_t *winH = reinterpret_cast<uint32_t *>(ws_smem + C::OFF_WINH);   // [TH][WS_WW] right-image H words
+	uint32_t *winH = reinterpret_cast<uint32_t *>(ws_smem + C::OFF_WINH);   // [TH][WS_WW] right-image H words (32-bit form)
+	uint16_t *winH16 = reinterpret_cast<uint16_t *>(ws_smem + C::OFF_WINH); // same, narrowed: 4L | 4(R-1) << 8
 	uint16_t *winV = reinterpret_cast<uint16_t *>(ws_smem + C::OFF_WINV);   // [WS_TY][WS_WW] right-image U | D << 8
 	float *mus = reinterpret_cast<float *>(ws_smem + C::OFF_MU);            // [WS_NST] centre value of the stage's tile
 	uint64_t *bar_full = reinterpret_cast<uint64_t *>(ws_smem + C::OFF_BAR);   // TMA landed
@@ -133,7 +139,8 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 	}
 	__syncthreads();
 
-	constexpr int W_PROD = WS_NWT / 32 + WS_NPW;       // producer warp index
+	constexpr bool MERGED = WS_HO < 32;                // no producer warp: prefix warp 0, lane 0 issues the TMA
+	constexpr int W_PROD = MERGED ? WS_NWT / 32 : WS_NWT / 32 + WS_NPW;   // warp whose lane 0 issues the TMA
 	if (warp == W_PROD && lane == 0) {                 // the first tiles fly while the arm windows are staged
 #pragma unroll
 		for (int s = 0; s < WS_NST; s++)
@@ -155,9 +162,14 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 				const int j = lane + 32 * m, xx = a1x0 + j;
 				if (j < WS_WW) {
 					const bool ok = rowok && xx >= 0 && xx < W;
-					const unsigned dst = (unsigned)__cvta_generic_to_shared(winH + r * WS_WW + j);
-					const int nbytes = ok ? 4 : 0;
-					asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(grow + (ok ? xx : 0)), "r"(nbytes));
+					if (C::H16) {
+						const uint32_t v = ok ? __ldg(grow + xx) : 0u;
+						winH16[r * WS_WW + j] = (uint16_t)((v & 255u) | ((v >> 8) & 0xff00u));
+					} else {
+						const unsigned dst = (unsigned)__cvta_generic_to_shared(winH + r * WS_WW + j);
+						const int nbytes = ok ? 4 : 0;
+						asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(grow + (ok ? xx : 0)), "r"(nbytes));
+					}
 				}
 			}
 		}
@@ -181,7 +193,7 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 	}
 	__syncthreads();                                   // windows visible to the walkers
 
-	if (warp == W_PROD) {
+	if (!MERGED && warp == W_PROD) {
 		// ---------------------------------------------------------------- producer
 		if (lane == 0) {
 			for (int dd = WS_NST; dd < nproc; dd++) {
@@ -216,12 +228,13 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 			}
 			// two independent row pairs per iteration (the scan of one is a chain of dependent adds and shuffles: a single
 			// pair per iteration left the prefix warps latency-bound and the walkers waiting for them)
-			for (int pr0 = pw; pr0 < (TH + 1) / 2; pr0 += 2 * WS_NPW) {
-				float v[2][EPL];
-				float *row[2];
-				bool act[2];
+			constexpr int UP = WS_NPW <= 3 ? 4 : 2;         // independent row pairs per iteration
+			for (int pr0 = pw; pr0 < (TH + 1) / 2; pr0 += UP * WS_NPW) {
+				float v[UP][EPL];
+				float *row[UP];
+				bool act[UP];
 #pragma unroll
-				for (int u = 0; u < 2; u++) {
+				for (int u = 0; u < UP; u++) {
 					const int r = 2 * (pr0 + u * WS_NPW) + half;
 					act[u] = r < TH;
 					row[u] = P + (act[u] ? r : 0) * TWP + li * EPL;
@@ -229,7 +242,7 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 					for (int i = 0; i < EPL; i++) v[u][i] = row[u][i];
 				}
 #pragma unroll
-				for (int u = 0; u < 2; u++) {
+				for (int u = 0; u < UP; u++) {
 					if (CENTER) {
 #pragma unroll
 						for (int i = 0; i < EPL; i++) v[u][i] -= mu;
@@ -240,39 +253,51 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 					}
 				}
 #pragma unroll
-				for (int i = 1; i < EPL; i++) {
-					v[0][i] += v[0][i - 1];
-					v[1][i] += v[1][i - 1];
-				}
-				float incl0 = v[0][EPL - 1], incl1 = v[1][EPL - 1];
+				for (int i = 1; i < EPL; i++)
+#pragma unroll
+					for (int u = 0; u < UP; u++) v[u][i] += v[u][i - 1];
+				float incl[UP];
+#pragma unroll
+				for (int u = 0; u < UP; u++) incl[u] = v[u][EPL - 1];
 #pragma unroll
 				for (int o = 1; o < 16; o <<= 1) {
-					const float up0 = __shfl_up_sync(0xffffffffu, incl0, o, 16);
-					const float up1 = __shfl_up_sync(0xffffffffu, incl1, o, 16);
+					float up[UP];
+#pragma unroll
+					for (int u = 0; u < UP; u++) up[u] = __shfl_up_sync(0xffffffffu, incl[u], o, 16);
 					if (li >= o) {
-						incl0 += up0;
-						incl1 += up1;
+#pragma unroll
+						for (int u = 0; u < UP; u++) incl[u] += up[u];
 					}
 				}
-				const float base0 = incl0 - v[0][EPL - 1], base1 = incl1 - v[1][EPL - 1];
-				if (act[0]) {
 #pragma unroll
-					for (int i = 0; i < EPL; i++) row[0][i] = v[0][i] + base0;
-				}
-				if (act[1]) {
+				for (int u = 0; u < UP; u++) {
+					const float base = incl[u] - v[u][EPL - 1];
+					if (act[u]) {
 #pragma unroll
-					for (int i = 0; i < EPL; i++) row[1][i] = v[1][i] + base1;
+						for (int i = 0; i < EPL; i++) row[u][i] = v[u][i] + base;
+					}
 				}
 			}
 			fence_proxy_async_smem();                      // generic writes of this stage before its next TMA refill
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&bar_ready[s]);
+			if (MERGED && pw == 0) {
+				// producer duty AFTER this plane's prefixes are published: plane dd + 2 goes into the stage the walkers
+				// release when they finish plane dd - 1 (they are walking it now; plane dd is already waiting for them)
+				if (lane == 0 && dd >= 1 && dd + WS_NST - 1 < nproc) {
+					const int nx = dd + WS_NST - 1, s2 = nx % WS_NST;
+					mbar_wait(&bar_empty[s2], ((nx / WS_NST) - 1) & 1);
+					mbar_arrive_expect_tx(&bar_full[s2], C::TILE_BYTES);
+					tma_load_3d(ws_smem + s2 * C::STAGE_BYTES, &tmap, x0 - HX, y0 - HALO, d0 + nx, &bar_full[s2]);
+				}
+				__syncwarp();
+			}
 		}
 		return;
 	}
 
 	// -------------------------------------------------------------------- walkers
-	const int c = tid & (WS_TX - 1), h = tid >> 7;      // column, half (output rows 32h .. 32h + 31)
+	const int c = tid & (WS_TX - 1), h = tid >> 7;      // column, row group (output rows HO h .. HO h + HO - 1)
 	const int x = x0 + c;
 	const int yb = y0 + WS_HO * h;                       // first output row of this thread
 	const int nv = x < W ? max(0, min(WS_HO, H - yb)) : 0;   // output rows of this thread inside the image
@@ -302,6 +327,7 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 		// column walk: relative row rr <-> tile row 32h + rr <-> image row yb - HALO + rr
 		const char *Pc = reinterpret_cast<const char *>(P + (WS_HO * h) * TWP + c + HX);   // own pixel's prefix entry, relative row 0
 		const uint32_t *wh = winH + (WS_HO * h) * WS_WW + c + off;
+		const uint16_t *wh16 = winH16 + (WS_HO * h) * WS_WW + c + off;
 		const uint16_t *wv = winV + (WS_HO * h) * WS_WW + c + off;
 		char *po = reinterpret_cast<char *>(out + ((long)d * H + yb) * ld + x);
 		const long ldb = (long)ld * 4;
@@ -320,7 +346,8 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 			for (int i = 0; i < WB; i++) {
 				const int rr = b0 + i;
 				if (rr <= NWALK) {
-					hw[i] = __vminu2(ah[rr - 1], wh[rr * WS_WW]);   // min of lengths = (max of left ends, min of right ends), :362-363
+					const uint32_t wr = C::H16 ? __byte_perm((uint32_t)wh16[rr * WS_WW], 0u, 0x4140) : wh[rr * WS_WW];
+					hw[i] = __vminu2(ah[rr - 1], wr);               // min of lengths = (max of left ends, min of right ends), :362-363
 					if (rr >= 2 * R + 1) {
 						const int k = rr - 2 * R - 1;
 						vw[i] = __vminu2(av[k], __byte_perm((uint32_t)wv[k * WS_WW], 0u, 0x1404));   // :359-360
@@ -348,7 +375,7 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 				if (CENTER && VMODE != 2) S = fmaf(mu, nf, S);
 				if (VMODE == 2) {
 					run = ws_add2(run, ws_pack2(S, nf));
-					*reinterpret_cast<unsigned long long *>(rgb + (rr & (C::RING - 1)) * RROW) = run;
+					*reinterpret_cast<unsigned long long *>(rgb + (rr % C::RING) * RROW) = run;
 				} else {
 					sn[rr] = ws_pack2(S, nf);
 				}
@@ -357,14 +384,23 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 					const unsigned U8 = vw[i] & 0xffffu, D8 = vw[i] >> 16;   // U << 8, Dn << 8
 					float T, N;
 					if (VMODE == 2) {
-						constexpr int M = C::RING - 1, RMASK = C::RING * RROW - 1;
+						constexpr int RING = C::RING, RB = RING * RROW;
+						constexpr int SC = RROW / 256;                 // U8 = U << 8: U8 * SC = U * RROW
 						const int rk = HALO + k;
 						// rows y - U + 1 .. y + Dn - 1 (:361): run(rk + Dn - 1) - run(rk - U); the ring index wraps only
-						// where the (compile-time) row position says it can.  U8 * 8 = U * RROW.
-						int oh = D8 * 8 + (((rk - 1) & M) * RROW);
-						if (((rk - 1) & M) + R + 1 > M) oh &= RMASK;
-						int ol = ((rk & M) * RROW) - U8 * 8;
-						if ((rk & M) - R - 1 < 0) ol = (ol + C::RING * RROW) & RMASK;
+						// where the (compile-time) row position says it can
+						constexpr bool POW2 = (RING & (RING - 1)) == 0;
+						const int sb = (rk - 1) % RING, sb2 = rk % RING;
+						int oh = D8 * SC + sb * RROW;
+						if (sb + R + 1 >= RING) {
+							if (POW2) oh &= RB - 1;
+							else oh = oh >= RB ? oh - RB : oh;
+						}
+						int ol = sb2 * RROW - U8 * SC;
+						if (sb2 - R - 1 < 0) {
+							if (POW2) ol = (ol + RB) & (RB - 1);
+							else ol = ol < 0 ? ol + RB : ol;
+						}
 						const float2 a = *reinterpret_cast<const float2 *>(rgb + oh), b = *reinterpret_cast<const float2 *>(rgb + ol);
 						T = a.x - b.x;
 						N = a.y - b.y;
@@ -421,17 +457,17 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 	}
 }
 
-template <int R, int WB, bool CENTER, int VMODE, int NPW>
+template <int R, int WB, bool CENTER, int VMODE, int NPW, int HO>
 int launch_ws(const CUtensorMap &tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
 	      cudaStream_t s)
 {
-	using C = WSCfg<R>;
+	using C = WSCfg<R, HO>;
 	constexpr int smem = VMODE == 2 ? C::SMEM_RING : C::SMEM_NORING;
 	static bool attr_done[64] = {false};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!attr_done[dev & 63]) {
-		ADC_CUDA(cudaFuncSetAttribute(cbca_ws_kernel<R, WB, CENTER, VMODE, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		ADC_CUDA(cudaFuncSetAttribute(cbca_ws_kernel<R, WB, CENTER, VMODE, NPW, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 		attr_done[dev & 63] = true;
 	}
 	static const int dch_env = getenv("ADCENSUS_CBCA_DCH") ? atoi(getenv("ADCENSUS_CBCA_DCH")) : 0;   // tuning knob, not part of the ABI
@@ -440,7 +476,7 @@ int launch_ws(const CUtensorMap &tm, const uint32_t *hv, const float *vol, float
 	dch = adc_div_up(D, adc_div_up(D, dch));               // equal chunks (19 x 12 at D = 228)
 	const long HW = (long)H * W;
 	dim3 grid(adc_div_up(W, WS_TX), adc_div_up(H, WS_TY), adc_div_up(D, dch));
-	cbca_ws_kernel<R, WB, CENTER, VMODE, NPW><<<grid, ws_nt(NPW), smem, s>>>(tm, hv, hv + 2 * HW, hv + HW, hv + 3 * HW, vol, out, D, H, W, ld, direction, dch);
+	cbca_ws_kernel<R, WB, CENTER, VMODE, NPW, HO><<<grid, ws_nt(NPW, HO), smem, s>>>(tm, hv, hv + 2 * HW, hv + HW, hv + 3 * HW, vol, out, D, H, W, ld, direction, dch);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
@@ -453,7 +489,7 @@ int adc_cbca_ws_max_halo() { return 4; }
 void adc_cbca_ws_box(int halo, int *box_w, int *box_h)
 {
 	*box_w = WS_TWP;
-	*box_h = halo <= 1 ? WSCfg<1>::TH : WSCfg<4>::TH;
+	*box_h = halo <= 1 ? WSCfg<1, 32>::TH : WSCfg<4, 32>::TH;
 }
 
 // hv: packed arms (adc_pack_arms_hv); tm: tensor map of `vol` with the box of adc_cbca_ws_box(halo)
@@ -466,18 +502,22 @@ int adc_cbca_ws(const CUtensorMap *tm, const uint32_t *hv, const float *vol, flo
 	static const int center = getenv("ADCENSUS_CBCA_CENTER") ? atoi(getenv("ADCENSUS_CBCA_CENTER")) : 1;
 	static const int vmode = getenv("ADCENSUS_CBCA_VMODE") ? atoi(getenv("ADCENSUS_CBCA_VMODE")) : 2;
 	static const int npw = getenv("ADCENSUS_CBCA_NPW") ? atoi(getenv("ADCENSUS_CBCA_NPW")) : 4;
-#define WS_GO(R_, WB_, C_, V_, N_) return launch_ws<R_, WB_, C_, V_, N_>(*tm, hv, vol, out, D, H, W, ld, direction, s)
+#define WS_GO(R_, WB_, C_, V_, N_, HO_) return launch_ws<R_, WB_, C_, V_, N_, HO_>(*tm, hv, vol, out, D, H, W, ld, direction, s)
+	static const int ho = getenv("ADCENSUS_CBCA_HO") ? atoi(getenv("ADCENSUS_CBCA_HO")) : 32;
 	if (halo <= 1) {
-		if (vmode == 2) { if (center) WS_GO(1, 6, true, 2, 4); else WS_GO(1, 6, false, 2, 4); }
-		if (center) WS_GO(1, 6, true, 1, 4); else WS_GO(1, 6, false, 1, 4);
+		if (vmode == 2) { if (center) WS_GO(1, 6, true, 2, 4, 32); else WS_GO(1, 6, false, 2, 4, 32); }
+		if (center) WS_GO(1, 6, true, 1, 4, 32); else WS_GO(1, 6, false, 1, 4, 32);
 	}
 	if (halo <= 4) {
-		if (npw == 6) {
-			if (vmode == 2) { if (center) WS_GO(4, 4, true, 2, 6); else WS_GO(4, 4, false, 2, 6); }
-			if (center) WS_GO(4, 4, true, 1, 6); else WS_GO(4, 4, false, 1, 6);
+		if (ho == 16) {                                    // 16 walker warps (column x quarter), ring mode only
+			if (center) WS_GO(4, 4, true, 2, 3, 16); else WS_GO(4, 4, false, 2, 3, 16);
 		}
-		if (vmode == 2) { if (center) WS_GO(4, 4, true, 2, 4); else WS_GO(4, 4, false, 2, 4); }
-		if (center) WS_GO(4, 4, true, 1, 4); else WS_GO(4, 4, false, 1, 4);
+		if (npw == 6) {
+			if (vmode == 2) { if (center) WS_GO(4, 4, true, 2, 6, 32); else WS_GO(4, 4, false, 2, 6, 32); }
+			if (center) WS_GO(4, 4, true, 1, 6, 32); else WS_GO(4, 4, false, 1, 6, 32);
+		}
+		if (vmode == 2) { if (center) WS_GO(4, 4, true, 2, 4, 32); else WS_GO(4, 4, false, 2, 4, 32); }
+		if (center) WS_GO(4, 4, true, 1, 4, 32); else WS_GO(4, 4, false, 1, 4, 32);
 	}
 #undef WS_GO
 	return ADCENSUS_ELIMIT;

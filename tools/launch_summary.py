@@ -49,7 +49,7 @@ if "--json" in sys.argv:
                 b += (sum(rd) / len(rd) + sum(wr) / len(wr)) * per_call
         return int(b * 1e6) if b else None
 
-    out = {"StereoJoin": tot("stereo_join_kernel"), "cbca_fast": tot("cbca_tma_kernel"), "cbca_exact": tot("cbca_win_kernel"),
+    out = {"StereoJoin": tot("stereo_join"), "cbca_fast": tot("cbca_ws_kernel") or tot("cbca_tma_kernel"), "cbca_exact": tot("cbca_win_kernel"),
            "transpose_in": tot("transpose_rows_kernel"), "transpose_out": tot("transpose_rows_kernel"), "argmin": tot("argmin_pitched_kernel"),
            "sgm2": (tot("sgm_class_kernel") or 0) + (tot("sgm_sel_kernel") or 0) + (tot("sgm_hpair_kernel") or 0) + (tot("sgm_pass_kernel") or 0),
            "source": "ncu launch list %s (dram__bytes_read.sum + dram__bytes_write.sum, mean per launch; sgm2 = class + selector + hpair + the "
