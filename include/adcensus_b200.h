@@ -269,6 +269,13 @@ int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const float *const *
 				  const float *const *featR_host, const float *const *imgL_host,
 				  const float *const *imgR_host, float *const *disp_host);
 
+/* n device-resident pairs (arrays of n device pointers each), ordered on `stream` as a whole.  Pairs alternate between two
+ * lanes (two buffer sets on internal streams, created on first use; ADCENSUS_LANES=1 disables the second lane), so that one
+ * pair's low-occupancy post-processing tail overlaps the next pair's volume kernels.  Results identical to n calls of
+ * mccnn_pipeline_run. */
+int mccnn_pipeline_run_batch(mccnn_pipeline *p, int n, const float *const *featL, const float *const *featR,
+			     const float *const *imgL, const float *const *imgR, float *const *disp, adcensus_stream_t stream);
+
 /* ---- the accurate ('slow') architecture's scorer head (csrc/scorer_head.cu) -------------------------------------
  * Replaces the per-disparity loop of main.lua:958-984 over net_te2 (main.lua:688-695: l2 x [SpatialConvolution1_fw,
  * ReLU], SpatialConvolution1_fw(nh2 -> 1), Sigmoid; SpatialConvolution1_fw.lua:11-31 = addmm + bias per pixel) by one

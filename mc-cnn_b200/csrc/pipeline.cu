@@ -11,6 +11,7 @@
 // Stage order, which volume is "left"/"right", the direction loop {+1,-1}, the /4
 // and the permutes follow main.lua line by line (cited inline); the kernels are
 // the ones behind the adcensus_* C ABI.
+#include <initializer_list>
 #include <math.h>
 #include <new>
 #include <stdlib.h>
@@ -92,6 +93,11 @@ struct mccnn_pipeline {
 	float *h_feat[2], *h_img[2], *h_disp[2];  // device copies per slot: 2F, 2HW, HW
 	cudaStream_t own_stream, copy_stream, out_stream;
 	cudaEvent_t ev_in[2], ev_free[2], ev_out[2];
+	// second lane of the batch entry points: a twin pipeline (own buffers and streams) that takes every other pair, so that the
+	// low-occupancy tail of one pair (LR check, interpolation, median, bilateral: ~0.6 ms of small kernels) and the bubbles
+	// between its launches run next to the heavy kernels of the next pair
+	mccnn_pipeline *twin;
+	cudaEvent_t ev_fork, ev_lane;
 };
 
 extern "C" int mccnn_pipeline_set_overlap(mccnn_pipeline *p, int mode);
@@ -221,6 +227,9 @@ extern "C" void mccnn_pipeline_destroy(mccnn_pipeline *p)
 		if (p->ev_out[k]) cudaEventDestroy(p->ev_out[k]);
 	}
 	overlap_release(p);
+	if (p->twin) mccnn_pipeline_destroy(p->twin);
+	if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+	if (p->ev_lane) cudaEventDestroy(p->ev_lane);
 	if (p->own_stream) cudaStreamDestroy(p->own_stream);
 	if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
 	if (p->out_stream) cudaStreamDestroy(p->out_stream);
@@ -452,10 +461,52 @@ static int host_staging(mccnn_pipeline *p)
 	return rc;
 }
 
-// n pairs from host memory (pinned for real overlap): pair i's inputs are copied on a copy stream
-// into staging slot i%2 while pair i-1 computes; its disparity map is copied back on the copy
-// stream while pair i+1 computes (separate H2D / kernel / D2H streams, two staging slots).
-// Returns when every result is in its host buffer.
+// the second lane (see struct): created on first use with the same parameters and modes; ADCENSUS_LANES=1 keeps one lane
+static mccnn_pipeline *batch_twin(mccnn_pipeline *p)
+{
+	static const int lanes = getenv("ADCENSUS_LANES") ? atoi(getenv("ADCENSUS_LANES")) : 2;
+	if (lanes < 2) return nullptr;
+	if (!p->twin) {
+		mccnn_pipeline *t = nullptr;
+		if (mccnn_pipeline_create(&t, p->C, p->D, p->H, p->W, &p->prm, p->device)) {
+			cudaGetLastError();
+			return nullptr;                            // not enough memory for a second lane: one lane gives the same results
+		}
+		p->twin = t;
+	}
+	p->twin->cbca_mode = p->cbca_mode;
+	p->twin->sgm_dhw = p->sgm_dhw;
+	if (p->twin->overlap != p->overlap) mccnn_pipeline_set_overlap(p->twin, p->overlap);
+	return p->twin;
+}
+
+// pair number j of lane q from host memory: inputs are copied on q's copy stream into staging slot j % 2 while the lane's
+// previous pair computes; the disparity map goes back on q's output stream
+static int enqueue_host_pair(mccnn_pipeline *q, int j, const float *featL, const float *featR, const float *imgL, const float *imgR, float *disp)
+{
+	const size_t F = (size_t)q->C * q->HW * sizeof(float), I = (size_t)q->HW * sizeof(float);
+	cudaStream_t cs = q->copy_stream, ks = q->own_stream, os = q->out_stream;  // H2D, kernels, D2H
+	const int k = j & 1;
+	float *fL = q->h_feat[k], *fR = fL + (size_t)q->C * q->HW;
+	float *iL = q->h_img[k], *iR = iL + q->HW;
+	if (j >= 2) ADC_CUDA(cudaStreamWaitEvent(cs, q->ev_free[k], 0));   // slot's previous pair consumed
+	ADC_CUDA(cudaMemcpyAsync(fL, featL, F, cudaMemcpyHostToDevice, cs));
+	ADC_CUDA(cudaMemcpyAsync(fR, featR, F, cudaMemcpyHostToDevice, cs));
+	ADC_CUDA(cudaMemcpyAsync(iL, imgL, I, cudaMemcpyHostToDevice, cs));
+	ADC_CUDA(cudaMemcpyAsync(iR, imgR, I, cudaMemcpyHostToDevice, cs));
+	ADC_CUDA(cudaEventRecord(q->ev_in[k], cs));
+	ADC_CUDA(cudaStreamWaitEvent(ks, q->ev_in[k], 0));
+	if (j >= 2) ADC_CUDA(cudaStreamWaitEvent(ks, q->ev_out[k], 0));     // slot's previous result copied out
+	STEP(mccnn_pipeline_run(q, fL, fR, iL, iR, q->h_disp[k], nullptr, nullptr, ks));
+	ADC_CUDA(cudaEventRecord(q->ev_free[k], ks));
+	ADC_CUDA(cudaStreamWaitEvent(os, q->ev_free[k], 0));
+	ADC_CUDA(cudaMemcpyAsync(disp, q->h_disp[k], I, cudaMemcpyDeviceToHost, os));
+	ADC_CUDA(cudaEventRecord(q->ev_out[k], os));
+	return 0;
+}
+
+// n pairs from host memory (pinned for real overlap): separate H2D / kernel / D2H streams with two staging slots per lane,
+// pairs alternating between two lanes (two buffer sets, see batch_twin).  Returns when every result is in its host buffer.
 extern "C" int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const float *const *featL_host,
 					     const float *const *featR_host, const float *const *imgL_host,
 					     const float *const *imgR_host, float *const *disp_host)
@@ -465,29 +516,54 @@ extern "C" int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const flo
 		if (!featL_host[i] || !featR_host[i] || !imgL_host[i] || !imgR_host[i] || !disp_host[i]) return ADCENSUS_EINVAL;
 	DeviceGuard g(p->device);
 	STEP(host_staging(p));
-	const size_t F = (size_t)p->C * p->HW * sizeof(float), I = (size_t)p->HW * sizeof(float);
-	cudaStream_t cs = p->copy_stream, ks = p->own_stream, os = p->out_stream;  // H2D, kernels, D2H
+	mccnn_pipeline *t = n > 1 ? batch_twin(p) : nullptr;
+	if (t) STEP(host_staging(t));
 	for (int i = 0; i < n; i++) {
-		const int k = i & 1;
-		float *fL = p->h_feat[k], *fR = fL + (size_t)p->C * p->HW;
-		float *iL = p->h_img[k], *iR = iL + p->HW;
-		if (i >= 2) ADC_CUDA(cudaStreamWaitEvent(cs, p->ev_free[k], 0));   // slot's previous pair consumed
-		ADC_CUDA(cudaMemcpyAsync(fL, featL_host[i], F, cudaMemcpyHostToDevice, cs));
-		ADC_CUDA(cudaMemcpyAsync(fR, featR_host[i], F, cudaMemcpyHostToDevice, cs));
-		ADC_CUDA(cudaMemcpyAsync(iL, imgL_host[i], I, cudaMemcpyHostToDevice, cs));
-		ADC_CUDA(cudaMemcpyAsync(iR, imgR_host[i], I, cudaMemcpyHostToDevice, cs));
-		ADC_CUDA(cudaEventRecord(p->ev_in[k], cs));
-		ADC_CUDA(cudaStreamWaitEvent(ks, p->ev_in[k], 0));
-		if (i >= 2) ADC_CUDA(cudaStreamWaitEvent(ks, p->ev_out[k], 0));     // slot's previous result copied out
-		STEP(mccnn_pipeline_run(p, fL, fR, iL, iR, p->h_disp[k], nullptr, nullptr, ks));
-		ADC_CUDA(cudaEventRecord(p->ev_free[k], ks));
-		ADC_CUDA(cudaStreamWaitEvent(os, p->ev_free[k], 0));
-		ADC_CUDA(cudaMemcpyAsync(disp_host[i], p->h_disp[k], I, cudaMemcpyDeviceToHost, os));
-		ADC_CUDA(cudaEventRecord(p->ev_out[k], os));
+		mccnn_pipeline *q = (t && (i & 1)) ? t : p;
+		STEP(enqueue_host_pair(q, t ? i >> 1 : i, featL_host[i], featR_host[i], imgL_host[i], imgR_host[i], disp_host[i]));
 	}
-	ADC_CUDA(cudaStreamSynchronize(os));
-	ADC_CUDA(cudaStreamSynchronize(ks));
-	ADC_CUDA(cudaStreamSynchronize(cs));
+	for (mccnn_pipeline *q : {p, t}) {
+		if (!q) continue;
+		ADC_CUDA(cudaStreamSynchronize(q->out_stream));
+		ADC_CUDA(cudaStreamSynchronize(q->own_stream));
+		ADC_CUDA(cudaStreamSynchronize(q->copy_stream));
+	}
+	return 0;
+}
+
+// n device-resident pairs, ordered on `stream` as a whole (everything enqueued before the call precedes it, everything after
+// it sees all n disparity maps): pairs alternate between the two lanes on their own streams.
+extern "C" int mccnn_pipeline_run_batch(mccnn_pipeline *p, int n, const float *const *featL, const float *const *featR,
+					const float *const *imgL, const float *const *imgR, float *const *disp, adcensus_stream_t stream)
+{
+	if (!p || n < 0 || (n > 0 && (!featL || !featR || !imgL || !imgR || !disp))) return ADCENSUS_EINVAL;
+	for (int i = 0; i < n; i++)
+		if (!featL[i] || !featR[i] || !imgL[i] || !imgR[i] || !disp[i]) return ADCENSUS_EINVAL;
+	DeviceGuard g(p->device);
+	cudaStream_t s = adc_stream(stream);
+	mccnn_pipeline *t = n > 1 ? batch_twin(p) : nullptr;
+	if (!t) {
+		for (int i = 0; i < n; i++) STEP(mccnn_pipeline_run(p, featL[i], featR[i], imgL[i], imgR[i], disp[i], nullptr, nullptr, s));
+		return 0;
+	}
+	STEP(host_staging(p));                                  // creates the lanes' own streams
+	STEP(host_staging(t));
+	if (!p->ev_fork) {
+		ADC_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+		ADC_CUDA(cudaEventCreateWithFlags(&p->ev_lane, cudaEventDisableTiming));
+	}
+	if (!t->ev_lane) ADC_CUDA(cudaEventCreateWithFlags(&t->ev_lane, cudaEventDisableTiming));
+	ADC_CUDA(cudaEventRecord(p->ev_fork, s));
+	ADC_CUDA(cudaStreamWaitEvent(p->own_stream, p->ev_fork, 0));
+	ADC_CUDA(cudaStreamWaitEvent(t->own_stream, p->ev_fork, 0));
+	for (int i = 0; i < n; i++) {
+		mccnn_pipeline *q = (i & 1) ? t : p;
+		STEP(mccnn_pipeline_run(q, featL[i], featR[i], imgL[i], imgR[i], disp[i], nullptr, nullptr, q->own_stream));
+	}
+	for (mccnn_pipeline *q : {p, t}) {
+		ADC_CUDA(cudaEventRecord(q->ev_lane, q->own_stream));
+		ADC_CUDA(cudaStreamWaitEvent(s, q->ev_lane, 0));
+	}
 	return 0;
 }
 

@@ -222,6 +222,22 @@ class StereoPipeline:
         adcensus._check(rc, n)
         return disp
 
+    def run_batch(self, pairs, disps=None):
+        """``pairs``: list of (featL, featR, imgL, imgR) DEVICE tensors.  One call for the whole list, ordered on torch's
+        current stream as a whole; pairs alternate between two internal lanes (mccnn_pipeline_run_batch) so that the
+        post-processing tail of one pair overlaps the volume kernels of the next.  Returns the list of device disparity maps."""
+        n = "mccnn_pipeline_run_batch"
+        k = len(pairs)
+        if disps is None:
+            disps = [torch.empty((self.H, self.W), device=pairs[0][0].device, dtype=torch.float32) for _ in range(k)]
+        arr = lambda ts, i: (ctypes.c_void_p * k)(*[adcensus._t(t, i, n).value for t in ts])
+        with torch.cuda.device(pairs[0][0].device):
+            rc = adcensus.lib().mccnn_pipeline_run_batch(
+                self._h, k, arr([p[0] for p in pairs], 1), arr([p[1] for p in pairs], 2), arr([p[2] for p in pairs], 3),
+                arr([p[3] for p in pairs], 4), arr(disps, 5), adcensus._stream(pairs[0][0]))
+        adcensus._check(rc, n)
+        return disps
+
     def run_host(self, featL, featR, imgL, imgR, disp=None):
         """Host (CPU, ideally pinned) float32 tensors in and out; synchronous.  This is the call
         a non-CUDA host (the Lua/FFI side) makes: H2D + pipeline + D2H inside."""
