@@ -293,6 +293,20 @@ void mccnn_scorer_head_destroy(mccnn_scorer_head *h);
 int mccnn_scorer_head_forward(const mccnn_scorer_head *h, const float *featL, const float *featR, float *volL, float *volR,
 			      int H, int W, int D, int nterms, adcensus_stream_t stream);
 
+/* ---- the feature tower in-library (csrc/feature_tower.cu) ------------------------------------------
+ * net_te at test time (main.lua:682-686 arch 'slow', 726-749 arch 'fast'): l1 x cudnn.SpatialConvolution(3x3, stride 1,
+ * pad 1) with ReLU between the layers; arch 'fast' ends with Normalize2 (adcensus.cu:1284-1308) instead of a ReLU.
+ * W[i] (fm, cin_i, 3, 3) row-major and b[i] (fm), i = 0 .. l1-1, DEVICE pointers (cudnn.SpatialConvolution's weight / bias).
+ * Layer 1 (n_in = 1 or 3 planes) is exact fp32; the fm -> fm layers are tcgen05 implicit GEMMs (nterms 3: bf16-split
+ * operands, fp32-grade; 1: plain bf16).  Limits: fm a multiple of 16 and <= 128, l1 <= 8. */
+typedef struct mccnn_feature_tower mccnn_feature_tower;
+int mccnn_feature_tower_create(mccnn_feature_tower **out, int n_in, int fm, int l1, int relu_last, int normalize,
+			       const float *const *W, const float *const *b, int device, adcensus_stream_t stream);
+void mccnn_feature_tower_destroy(mccnn_feature_tower *h);
+/* img (nimg, n_in, H, W) -> out (nimg, fm, H, W); nimg = 2 for x_batch of main.lua:944. */
+int mccnn_feature_tower_forward(const mccnn_feature_tower *h, const float *img, float *out, int nimg, int H, int W,
+				int nterms, adcensus_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,8 @@ from BASELINE.json's wording:
 The operators are injected (``ops``), so the same driver runs on the CUDA library (CudaOps) and,
 in the CPU tests, on any object with the same methods over CPU tensors.
 """
+import math
+
 import torch
 import torch.distributed as dist
 
@@ -115,7 +117,9 @@ def stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm=None, chu
     if N > 1:
         assert band_min >= max(halo, 1), "bands thinner than the CBCA halo"
         assert max_arm <= 14, "row-band CBCA supports arms up to 14 pixels"
-    K = chunks if chunks else max(1, min(4 * N, W // 32)) if N > 1 else 1
+    # column chunks of the vertical wavefront: a chunk's scan is latency-bound (Hb serial steps) unless it is wide, and the chain
+    # costs (N - 1 + K) chunk times: K = N is the measured sweet spot (K = 4 N made 39 hops of 94 columns at Middlebury size)
+    K = chunks if chunks else max(1, min(N, W // 32)) if N > 1 else 1
 
     # first CBCA block on the band extended by cbca_i1 * halo rows: StereoJoin covers the extension (features are replicated)
     e1 = halo * int(opt.cbca_i1)
@@ -175,7 +179,8 @@ def stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm=None, chu
 
     disp = {}
     vol_left = None
-    for direction in (1, -1):                                                                        # :955
+    # main.lua:954-955: without the LR check (mb) only direction -1 is consumed
+    for direction in ((1, -1) if opt.lr_check else (-1,)):                                           # :955
         ext = volL if direction == -1 else volR                                                      # :986
         ext = cbca_block(ext, ya, yb, int(opt.cbca_i1), direction)                                   # :998-1001
         vol = ext[:, y0 - ya: y0 - ya + Hb].contiguous() if (ya != y0 or yb != y1) else ext
@@ -199,8 +204,17 @@ def stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm=None, chu
         d = ops.interpolate_mismatch(d, outlier)
     sub = ops.subpixel(d[y0:y1].contiguous(), vol_left, D)                                           # :1068 (band-local)
     d = comm.all_gather_rows(sub, H)
-    d = ops.median2d(d, 5)                                                                           # :1073
-    return ops.mean2d(d, opt.blur_sigma, opt.blur_t)                                                 # :1078
+
+    def band_filter(fn, full, r):
+        """an H x W filter of radius r rows computed for this rank's rows only (on the band extended by r rows of the gathered
+        map: the slice's edges are image edges exactly where the image ends), then gathered again"""
+        a, b = max(0, y0 - r), min(H, y1 + r)
+        o = fn(full[a:b].contiguous())
+        return comm.all_gather_rows(o[y0 - a: y0 - a + Hb].contiguous(), H)
+
+    d = band_filter(lambda t: ops.median2d(t, 5), d, 2)                                              # :1073
+    kr = int(math.ceil(float(opt.blur_sigma) * 3))                                                   # main.lua:529: kernel radius
+    return band_filter(lambda t: ops.mean2d(t, opt.blur_sigma, opt.blur_t), d, kr)                   # :1078
 
 
 class CudaOps:

@@ -51,3 +51,14 @@ def test_receptive_field_is_the_window():
     x3[0, 0, 10 + 1, 10 - 1] += 1.0                                             # well inside (ReLUs may gate the far corner)
     assert np.array_equal(ft.tower_forward(x2, layers, normalize=False)[0, :, 10, 10], base[0, :, 10, 10])
     assert not np.array_equal(ft.tower_forward(x3, layers, normalize=False)[0, :, 10, 10], base[0, :, 10, 10])
+
+
+def test_against_the_pytorch_restatement_fixture():
+    """tests/golden/feature_tower.npz: the module stack of main.lua:726-749 + Normalize_forward restated in PyTorch (CPU fp32),
+    generator oracle/make_feature_tower_golden.py"""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "feature_tower.npz"))
+    layers = [(g["w%d" % i], g["b%d" % i]) for i in range(4)]
+    got = ft.tower_forward(g["x"], layers)
+    assert np.abs(got - g["out"]).max() < 2e-6
