@@ -93,7 +93,7 @@ struct mccnn_pipeline {
 	float *h_feat[2], *h_img[2], *h_disp[2];  // device copies per slot: 2F, 2HW, HW
 	cudaStream_t own_stream, copy_stream, out_stream;
 	cudaEvent_t ev_in[2], ev_free[2], ev_out[2];
-	// second lane of the batch entry points: a twin pipeline (own buffers and streams) that takes every other pair, so that the
+	// further lanes of the batch entry points: a chain of twin pipelines (own buffers and streams) taking pairs round-robin, so that the
 	// low-occupancy tail of one pair (LR check, interpolation, median, bilateral: ~0.6 ms of small kernels) and the bubbles
 	// between its launches run next to the heavy kernels of the next pair
 	mccnn_pipeline *twin;
@@ -461,23 +461,31 @@ static int host_staging(mccnn_pipeline *p)
 	return rc;
 }
 
-// the second lane (see struct): created on first use with the same parameters and modes; ADCENSUS_LANES=1 keeps one lane
-static mccnn_pipeline *batch_twin(mccnn_pipeline *p)
+// the extra lanes (see struct): a chain of twins created on first use with the same parameters and modes.  ADCENSUS_LANES
+// (1..4, default 2) sets the number of lanes; lane 0 is the pipeline itself.
+static int batch_lanes(mccnn_pipeline *p, mccnn_pipeline **lane, int want)
 {
-	static const int lanes = getenv("ADCENSUS_LANES") ? atoi(getenv("ADCENSUS_LANES")) : 2;
-	if (lanes < 2) return nullptr;
-	if (!p->twin) {
-		mccnn_pipeline *t = nullptr;
-		if (mccnn_pipeline_create(&t, p->C, p->D, p->H, p->W, &p->prm, p->device)) {
-			cudaGetLastError();
-			return nullptr;                            // not enough memory for a second lane: one lane gives the same results
+	static const int lanes_env = getenv("ADCENSUS_LANES") ? atoi(getenv("ADCENSUS_LANES")) : 2;
+	int nl = lanes_env < 1 ? 1 : (lanes_env > 4 ? 4 : lanes_env);
+	if (nl > want) nl = want;
+	lane[0] = p;
+	int n = 1;
+	for (mccnn_pipeline *q = p; n < nl; n++) {
+		if (!q->twin) {
+			mccnn_pipeline *t = nullptr;
+			if (mccnn_pipeline_create(&t, p->C, p->D, p->H, p->W, &p->prm, p->device)) {
+				cudaGetLastError();
+				break;                                 // not enough memory for another lane: fewer lanes give the same results
+			}
+			q->twin = t;
 		}
-		p->twin = t;
+		q = q->twin;
+		q->cbca_mode = p->cbca_mode;
+		q->sgm_dhw = p->sgm_dhw;
+		if (q->overlap != p->overlap) mccnn_pipeline_set_overlap(q, p->overlap);
+		lane[n] = q;
 	}
-	p->twin->cbca_mode = p->cbca_mode;
-	p->twin->sgm_dhw = p->sgm_dhw;
-	if (p->twin->overlap != p->overlap) mccnn_pipeline_set_overlap(p->twin, p->overlap);
-	return p->twin;
+	return n;
 }
 
 // pair number j of lane q from host memory: inputs are copied on q's copy stream into staging slot j % 2 while the lane's
@@ -506,7 +514,7 @@ static int enqueue_host_pair(mccnn_pipeline *q, int j, const float *featL, const
 }
 
 // n pairs from host memory (pinned for real overlap): separate H2D / kernel / D2H streams with two staging slots per lane,
-// pairs alternating between two lanes (two buffer sets, see batch_twin).  Returns when every result is in its host buffer.
+// pairs round-robin over the lanes (buffer sets, see batch_lanes).  Returns when every result is in its host buffer.
 extern "C" int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const float *const *featL_host,
 					     const float *const *featR_host, const float *const *imgL_host,
 					     const float *const *imgR_host, float *const *disp_host)
@@ -515,18 +523,15 @@ extern "C" int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const flo
 	for (int i = 0; i < n; i++)
 		if (!featL_host[i] || !featR_host[i] || !imgL_host[i] || !imgR_host[i] || !disp_host[i]) return ADCENSUS_EINVAL;
 	DeviceGuard g(p->device);
-	STEP(host_staging(p));
-	mccnn_pipeline *t = n > 1 ? batch_twin(p) : nullptr;
-	if (t) STEP(host_staging(t));
-	for (int i = 0; i < n; i++) {
-		mccnn_pipeline *q = (t && (i & 1)) ? t : p;
-		STEP(enqueue_host_pair(q, t ? i >> 1 : i, featL_host[i], featR_host[i], imgL_host[i], imgR_host[i], disp_host[i]));
-	}
-	for (mccnn_pipeline *q : {p, t}) {
-		if (!q) continue;
-		ADC_CUDA(cudaStreamSynchronize(q->out_stream));
-		ADC_CUDA(cudaStreamSynchronize(q->own_stream));
-		ADC_CUDA(cudaStreamSynchronize(q->copy_stream));
+	mccnn_pipeline *lane[4];
+	const int nl = batch_lanes(p, lane, n > 1 ? n : 1);
+	for (int l = 0; l < nl; l++) STEP(host_staging(lane[l]));
+	for (int i = 0; i < n; i++)
+		STEP(enqueue_host_pair(lane[i % nl], i / nl, featL_host[i], featR_host[i], imgL_host[i], imgR_host[i], disp_host[i]));
+	for (int l = 0; l < nl; l++) {
+		ADC_CUDA(cudaStreamSynchronize(lane[l]->out_stream));
+		ADC_CUDA(cudaStreamSynchronize(lane[l]->own_stream));
+		ADC_CUDA(cudaStreamSynchronize(lane[l]->copy_stream));
 	}
 	return 0;
 }
@@ -541,28 +546,26 @@ extern "C" int mccnn_pipeline_run_batch(mccnn_pipeline *p, int n, const float *c
 		if (!featL[i] || !featR[i] || !imgL[i] || !imgR[i] || !disp[i]) return ADCENSUS_EINVAL;
 	DeviceGuard g(p->device);
 	cudaStream_t s = adc_stream(stream);
-	mccnn_pipeline *t = n > 1 ? batch_twin(p) : nullptr;
-	if (!t) {
+	mccnn_pipeline *lane[4];
+	const int nl = batch_lanes(p, lane, n > 1 ? n : 1);
+	if (nl == 1) {
 		for (int i = 0; i < n; i++) STEP(mccnn_pipeline_run(p, featL[i], featR[i], imgL[i], imgR[i], disp[i], nullptr, nullptr, s));
 		return 0;
 	}
-	STEP(host_staging(p));                                  // creates the lanes' own streams
-	STEP(host_staging(t));
-	if (!p->ev_fork) {
-		ADC_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-		ADC_CUDA(cudaEventCreateWithFlags(&p->ev_lane, cudaEventDisableTiming));
+	for (int l = 0; l < nl; l++) {
+		STEP(host_staging(lane[l]));                        // creates the lanes' own streams
+		if (!lane[l]->ev_lane) ADC_CUDA(cudaEventCreateWithFlags(&lane[l]->ev_lane, cudaEventDisableTiming));
 	}
-	if (!t->ev_lane) ADC_CUDA(cudaEventCreateWithFlags(&t->ev_lane, cudaEventDisableTiming));
+	if (!p->ev_fork) ADC_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
 	ADC_CUDA(cudaEventRecord(p->ev_fork, s));
-	ADC_CUDA(cudaStreamWaitEvent(p->own_stream, p->ev_fork, 0));
-	ADC_CUDA(cudaStreamWaitEvent(t->own_stream, p->ev_fork, 0));
+	for (int l = 0; l < nl; l++) ADC_CUDA(cudaStreamWaitEvent(lane[l]->own_stream, p->ev_fork, 0));
 	for (int i = 0; i < n; i++) {
-		mccnn_pipeline *q = (i & 1) ? t : p;
+		mccnn_pipeline *q = lane[i % nl];
 		STEP(mccnn_pipeline_run(q, featL[i], featR[i], imgL[i], imgR[i], disp[i], nullptr, nullptr, q->own_stream));
 	}
-	for (mccnn_pipeline *q : {p, t}) {
-		ADC_CUDA(cudaEventRecord(q->ev_lane, q->own_stream));
-		ADC_CUDA(cudaStreamWaitEvent(s, q->ev_lane, 0));
+	for (int l = 0; l < nl; l++) {
+		ADC_CUDA(cudaEventRecord(lane[l]->ev_lane, lane[l]->own_stream));
+		ADC_CUDA(cudaStreamWaitEvent(s, lane[l]->ev_lane, 0));
 	}
 	return 0;
 }

@@ -21,6 +21,7 @@ ap.add_argument("--D", type=int, default=228)
 ap.add_argument("--H", type=int, default=370)
 ap.add_argument("--W", type=int, default=1226)
 ap.add_argument("--C", type=int, default=64)
+ap.add_argument("--batch", action="store_true", help="one mccnn_pipeline_run_batch call for all iterations (lanes: ADCENSUS_LANES)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 opt = pipeline.make_params("kitti", a.preset)
@@ -34,13 +35,18 @@ if a.overlap >= 0:
     sp.set_overlap(a.overlap)
 for _ in range(3):
     sp.run(fL, fR, iL, iR)
+if a.batch:
+    sp.run_batch([(fL, fR, iL, iR)] * 4)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(a.iters):
-    sp.run(fL, fR, iL, iR)
+if a.batch:
+    sp.run_batch([(fL, fR, iL, iR)] * a.iters)
+else:
+    for _ in range(a.iters):
+        sp.run(fL, fR, iL, iR)
 e1.record()
 torch.cuda.synchronize()
-print("preset=%s dch=%s cbca=%s overlap=%s ms_per_pair=%.4f launches=%d" % (a.preset, os.environ.get("ADCENSUS_CBCA_DCH", "default"), sp.cbca_mode,
+print("preset=%s lanes=%s cbca=%s overlap=%s ms_per_pair=%.4f launches=%d" % (a.preset, (os.environ.get("ADCENSUS_LANES", "2") if a.batch else "-"), sp.cbca_mode,
                                                                     a.overlap, e0.elapsed_time(e1) / a.iters, sp.launches_per_run))
 sp.close()
