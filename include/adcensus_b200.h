@@ -269,6 +269,11 @@ int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const float *const *
 				  const float *const *featR_host, const float *const *imgL_host,
 				  const float *const *imgR_host, float *const *disp_host);
 
+/* Operator-level calls take their scratch (SGM tables, packed arms) stream-ordered from the device's default memory pool; the
+ * library raises that pool's release threshold to 2 GiB (never lowers it) so that repeated calls reuse the memory.
+ * adcensus_trim_scratch() hands everything unused back to the driver. */
+int adcensus_trim_scratch(void);
+
 /* n device-resident pairs (arrays of n device pointers each), ordered on `stream` as a whole.  Pairs alternate between two
  * lanes (two buffer sets on internal streams, created on first use; ADCENSUS_LANES=1 disables the second lane), so that one
  * pair's low-occupancy post-processing tail overlaps the next pair's volume kernels.  Results identical to n calls of

@@ -53,12 +53,19 @@ def run_sharded(n_items, compute, rank=None, world=None, gather=True, device="cp
     for k in range(rounds):
         idx = rank + k * world
         have = idx < n_items
-        ref = next(iter(local.values())) if local else None
-        shape = torch.tensor(list(local[idx].shape) if have else ([0] * (ref.dim() if ref is not None else 1)),
-                             dtype=torch.int64, device=device)
+        # fixed-length shape record [ndim, d0 .. d6]: every rank sends the same number of elements even when it owns no item
+        # in this round (n_items < world) or items of different rank
+        rec = [0] * 8
+        if have:
+            shp0 = list(local[idx].shape)
+            assert len(shp0) <= 7, "run_sharded gathers tensors of at most 7 dimensions"
+            rec[0] = len(shp0)
+            rec[1:1 + len(shp0)] = shp0
+        shape = torch.tensor(rec, dtype=torch.int64, device=device)
         shapes = [torch.zeros_like(shape) for _ in range(world)]
         dist.all_gather(shapes, shape)
-        numel = max(int(torch.prod(s).item()) for s in shapes)
+        shapes = [s[1:1 + int(s[0])] for s in shapes]
+        numel = max([int(torch.prod(s).item()) if s.numel() else 0 for s in shapes] + [1])
         buf = torch.zeros(numel, dtype=torch.float32, device=device)
         if have:
             buf[: local[idx].numel()] = local[idx].reshape(-1).to(device)

@@ -23,8 +23,11 @@ int adc_scratch_alloc(void **p, size_t bytes, cudaStream_t s)
 	if (cudaGetDevice(&dev) == cudaSuccess && !tuned[dev & 63]) {
 		cudaMemPool_t pool;
 		if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-			unsigned long long keep = ~0ULL;
-			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+			// bounded: a drop-in library must not pin unlimited memory in a pool the host application (torch's
+			// caching allocator, cutorch) cannot reuse; adcensus_trim_scratch() returns it on demand
+			unsigned long long keep = 2ULL << 30, cur = 0;
+			cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur);
+			if (cur < keep) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 		}
 		tuned[dev & 63] = true;
 	}
@@ -34,6 +37,17 @@ int adc_scratch_alloc(void **p, size_t bytes, cudaStream_t s)
 int adc_scratch_free(void *p, cudaStream_t s)
 {
 	return p ? (int)cudaFreeAsync(p, s) : 0;
+}
+
+// give the stream-ordered scratch kept by the operator-level calls back to the driver (after the work using it has completed)
+extern "C" int adcensus_trim_scratch(void)
+{
+	int dev = 0;
+	cudaMemPool_t pool;
+	ADC_CUDA(cudaGetDevice(&dev));
+	ADC_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+	ADC_CUDA(cudaMemPoolTrimTo(pool, 0));
+	return 0;
 }
 
 extern "C" const char *adcensus_version(void) { return "libadcensus_b200 0.1.0 (sm_100a)"; }

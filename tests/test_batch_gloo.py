@@ -51,7 +51,7 @@ def _worker(rank, world, port, n_items, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_items", [5, 4])
+@pytest.mark.parametrize("n_items", [5, 4, 1])      # 1: a rank that owns nothing still takes part in the gather
 def test_sharded_batch_world2(tmp_path, n_items):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, n_items, str(tmp_path)), nprocs=2, join=True)
