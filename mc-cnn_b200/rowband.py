@@ -187,7 +187,7 @@ def stereo_predict_rowband(ops, featL, featR, imgL, imgR, D, opt, comm=None, chu
         for _ in range(opt.sgm_i):                                                                   # :1008-1020
             tab = ops.sgm_tables(imgL, imgR, D, opt, direction)
             cost = ops.to_hwd(vol)                                                                   # (Hb, W, D)
-            acc = ops.zeros_like(cost)                                                               # :1014
+            acc = getattr(ops, "new_acc", ops.zeros_like)(cost)                                      # :1014 (zero by contract, see new_acc)
             ops.sgm_rows(tab, cost, acc, H, y0, opt, direction, 3, True, 0, W, None, None)           # right, left: band-local
             vertical_wavefront(tab, cost, acc, direction, 2)                                         # down
             vertical_wavefront(tab, cost, acc, direction, 3)                                         # up
@@ -263,6 +263,11 @@ class CudaOps:
 
     def zeros_like(self, t):
         return torch.zeros_like(t)
+
+    def new_acc(self, t):
+        """the SGM accumulator of main.lua:1014: the first launch on it is the horizontal pair with zero_out = True, which never
+        reads it and writes every element -- no memset needed on this backend"""
+        return torch.empty_like(t)
 
     def sgm_band(self, imgL, imgR, cost, acc, Ht, Wt, yoff, xoff, opt, direction, pass_mask, zero_out):
         import ctypes
