@@ -490,10 +490,12 @@ static int batch_lanes(mccnn_pipeline *p, mccnn_pipeline **lane, int want)
 
 // pair number j of lane q from host memory: inputs are copied on q's copy stream into staging slot j % 2 while the lane's
 // previous pair computes; the disparity map goes back on q's output stream
-static int enqueue_host_pair(mccnn_pipeline *q, int j, const float *featL, const float *featR, const float *imgL, const float *imgR, float *disp)
+// cs: the H2D stream SHARED by the lanes (copies of different lanes would otherwise split the PCIe bandwidth and both arrive late:
+// in order, pair i lands one transfer time after pair i - 1)
+static int enqueue_host_pair(mccnn_pipeline *q, int j, cudaStream_t cs, const float *featL, const float *featR, const float *imgL, const float *imgR, float *disp)
 {
 	const size_t F = (size_t)q->C * q->HW * sizeof(float), I = (size_t)q->HW * sizeof(float);
-	cudaStream_t cs = q->copy_stream, ks = q->own_stream, os = q->out_stream;  // H2D, kernels, D2H
+	cudaStream_t ks = q->own_stream, os = q->out_stream;  // kernels, D2H
 	const int k = j & 1;
 	float *fL = q->h_feat[k], *fR = fL + (size_t)q->C * q->HW;
 	float *iL = q->h_img[k], *iR = iL + q->HW;
@@ -527,7 +529,7 @@ extern "C" int mccnn_pipeline_run_host_batch(mccnn_pipeline *p, int n, const flo
 	const int nl = batch_lanes(p, lane, n > 1 ? n : 1);
 	for (int l = 0; l < nl; l++) STEP(host_staging(lane[l]));
 	for (int i = 0; i < n; i++)
-		STEP(enqueue_host_pair(lane[i % nl], i / nl, featL_host[i], featR_host[i], imgL_host[i], imgR_host[i], disp_host[i]));
+		STEP(enqueue_host_pair(lane[i % nl], i / nl, p->copy_stream, featL_host[i], featR_host[i], imgL_host[i], imgR_host[i], disp_host[i]));
 	for (int l = 0; l < nl; l++) {
 		ADC_CUDA(cudaStreamSynchronize(lane[l]->out_stream));
 		ADC_CUDA(cudaStreamSynchronize(lane[l]->own_stream));
