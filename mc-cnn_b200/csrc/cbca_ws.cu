@@ -91,6 +91,27 @@ __device__ __forceinline__ unsigned long long ws_add2(unsigned long long a, unsi
 	return d;
 }
 
+// planes [da, db) of the tile (x0, y0): out = vol (the entries with x + d * direction outside the image, :353-354), as aligned
+// float4 copies with 8 independent loads in flight per thread (rows start 16-byte aligned: x0 % 128 == 0, ld % 4 == 0)
+__device__ __forceinline__ void ws_copy_planes(const float *__restrict__ vol, float *__restrict__ out, int da, int db, int x0, int y0,
+					       int H, int W, int ld, int tid, int nthreads)
+{
+	constexpr int Q = WS_TX / 4;                             // float4 per tile row
+	const int total = (db - da) * WS_TY * Q;
+#pragma unroll 8
+	for (int i = tid; i < total; i += nthreads) {
+		const int q = i % Q, r = (i / Q) % WS_TY, d = da + i / (Q * WS_TY);
+		const int y = y0 + r, x = x0 + 4 * q;
+		if (y >= H || x >= W) continue;
+		const long idx = ((long)d * H + y) * ld + x;
+		if (x + 3 < W) {
+			*reinterpret_cast<float4 *>(out + idx) = __ldg(reinterpret_cast<const float4 *>(vol + idx));
+		} else {
+			for (int e = 0; x + e < W; e++) out[idx + e] = __ldg(vol + idx + e);
+		}
+	}
+}
+
 // CENTER: subtract one value per tile (the tile's mid pixel, 0 when that is not finite) before the row prefix and add
 // it back per run (mu * length): the prefixes then carry deviations instead of the level of the plane.
 // VMODE: how an output gathers its rows y - U + 1 .. y + Dn - 1:
@@ -127,6 +148,10 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 	int nproc = 0;
 	while (nproc < dn && !(direction < 0 ? (x0 + WS_TX - 1 - (d0 + nproc) < 0) : (x0 + d0 + nproc >= W))) nproc++;
 
+	if (nproc == 0) {                                      // the whole chunk lies in the invalid triangle: a plain copy, no staging
+		ws_copy_planes(vol, out, d0, d0 + dn, x0, y0, H, W, ld, tid, WS_NT);
+		return;
+	}
 	if (tid == 0) {
 #pragma unroll
 		for (int s = 0; s < WS_NST; s++) {
@@ -150,9 +175,10 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 			}
 	}
 
-	// right-image arm windows (once per CTA), 0 outside the image: a warp per window row, lanes along x
-	{
-		constexpr int NW = WS_NT / 32, NCH = (WS_WW + 31) / 32;
+	// right-image arm windows (once per CTA), 0 outside the image: a warp per window row, lanes along x.  Only the walkers
+	// need them: they stage them among themselves (named barrier) while the prefix warps already work on the first tile
+	if (warp < WS_NWT / 32) {
+		constexpr int NW = WS_NWT / 32, NCH = (WS_WW + 31) / 32;
 		for (int r = warp; r < TH; r += NW) {
 			const int yy = y0 - HALO + r;
 			const bool rowok = yy >= 0 && yy < H;
@@ -190,8 +216,8 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 			}
 		}
 		asm volatile("cp.async.wait_group 0;");
+		asm volatile("bar.sync 2, %0;" ::"n"(WS_NWT) : "memory");   // windows visible to the walkers
 	}
-	__syncthreads();                                   // windows visible to the walkers
 
 	if (!MERGED && warp == W_PROD) {
 		// ---------------------------------------------------------------- producer
@@ -438,6 +464,7 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 		}
 		if (!valid_col && nv > 0) {                        // x + d*direction outside the image: plain copy, keeps NaN (:353-354)
 			const long idx0 = ((long)d * H + yb) * ld + x;
+#pragma unroll 8
 			for (int k = 0; k < nv; k++) out[idx0 + (long)k * ld] = __ldg(vol + idx0 + (long)k * ld);
 		}
 		// the walkers only READ the stage: the mbarrier release / acquire orders those reads before the refill (the
@@ -446,14 +473,8 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 		__syncwarp();
 		if (lane == 0) mbar_arrive(&bar_empty[s]);
 	}
-	for (int dd = nproc; dd < dn; dd++) {                  // tiles entirely inside the invalid triangle: plain copy
-		const int d = d0 + dd;
-#pragma unroll 4
-		for (int k = 0; k < WS_HO; k++) {
-			const int y = yb + k;
-			const long idx = ((long)d * H + y) * ld + x;
-			if (y < H && x < W) out[idx] = __ldg(vol + idx);
-		}
+	if (nproc < dn) {                                      // planes entirely inside the invalid triangle: plain copy
+		ws_copy_planes(vol, out, d0 + nproc, d0 + dn, x0, y0, H, W, ld, tid, WS_NWT);
 	}
 }
 
