@@ -37,25 +37,27 @@ __host__ __device__ constexpr int ws_nwt(int ho) { return WS_TX * (WS_TY / ho); 
 __host__ __device__ constexpr int ws_nt(int npw, int ho) { return ws_nwt(ho) + 32 * npw + (ho < 32 ? 0 : 32); }
 constexpr int WS_DCH = 20;                  // max disparities per CTA
 constexpr int WS_WW = WS_TX + WS_DCH;       // pitch of the right-image arm windows
-constexpr int WS_NST = 3;                   // tile stages
 constexpr int WS_TWP = 144;                 // tile pitch = TMA box width: 16 lanes x 9 columns, = 16 (mod 32)
 
-template <int R, int HO>
+// LEAN: two tile stages and a 16-bit H-word window: 150 KB instead of 216 KB of shared memory, which leaves room for an SGM /
+// transpose CTA of the other direction (or lane) on the same SM -- the issue-bound walk and the HBM-bound scans overlap
+template <int R, int HO, bool LEAN>
 struct WSCfg {
+	static constexpr int NST = LEAN ? 2 : 3;           // tile stages
 	static constexpr int HALO = R + 1;                 // the prefix differences index the first EXCLUDED pixel
 	static constexpr int HX = (HALO + 3) & ~3;         // left halo in columns (TMA: 16-byte aligned start along x)
 	static constexpr int TH = WS_TY + 2 * R + 1;       // image rows y0 - HALO .. y0 + TY + R - 1
 	static constexpr int NWALK = 2 * R + HO;           // rows a thread walks for its HO outputs
 	static constexpr int NWT = ws_nwt(HO);
-	static constexpr bool H16 = HO < 32;               // narrow the H-word window to 16 bits (shared-memory budget of the 512-thread form)
+	static constexpr bool H16 = HO < 32 || LEAN;       // narrow the H-word window to 16 bits (shared-memory budget)
 	static constexpr int TILE_BYTES = TH * WS_TWP * 4; // bytes one TMA box delivers
 	static constexpr int STAGE_BYTES = (TILE_BYTES + 127) & ~127;
-	static constexpr int OFF_WINH = WS_NST * STAGE_BYTES;
+	static constexpr int OFF_WINH = NST * STAGE_BYTES;
 	static constexpr int OFF_WINV = OFF_WINH + ((TH * WS_WW * (H16 ? 2 : 4) + 15) & ~15);
 	static constexpr int OFF_MU = OFF_WINV + ((WS_TY * WS_WW * 2 + 15) & ~15);
 	static constexpr int OFF_BAR = OFF_MU + 16;
-	static constexpr int OFF_RING = OFF_BAR + ((3 * WS_NST * 8 + 15) & ~15);   // VMODE 2 only: [RING][NWT] (T, N) per thread
-	static constexpr int RING = HO < 32 ? 2 * R + 2 : 16;   // a power of two where the budget allows (cheaper wrap)
+	static constexpr int OFF_RING = OFF_BAR + ((3 * NST * 8 + 15) & ~15);   // VMODE 2 only: [RING][NWT] (T, N) per thread
+	static constexpr int RING = (HO < 32 || LEAN) ? 2 * R + 2 : 16;   // a power of two where the budget allows (cheaper wrap)
 	static constexpr int SMEM_NORING = OFF_RING;
 	static constexpr int SMEM_RING = OFF_RING + RING * NWT * 8;
 	static_assert(SMEM_RING <= 232448, "shared memory budget");
@@ -119,7 +121,7 @@ __device__ __forceinline__ void ws_copy_planes(const float *__restrict__ vol, fl
 //   2  running (T, N) down the column in a per-thread shared-memory ring, output = difference of two entries (fewest
 //      instructions, most shared-memory traffic); with CENTER the running sums carry deviations only
 // (predicated add.rn.f32x2 was tried first: ptxas turns each into FADD2 + 2 SEL, 70 instructions per output)
-template <int R, int WB, bool CENTER, int VMODE, int WS_NPW, int WS_HO>
+template <int R, int WB, bool CENTER, int VMODE, int WS_NPW, int WS_HO, bool LEAN>
 __global__ void __launch_bounds__(ws_nt(WS_NPW, WS_HO), 1)
 cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 	       const uint32_t *__restrict__ a0h, const uint32_t *__restrict__ a0v,
@@ -127,8 +129,8 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 	       const float *__restrict__ vol, float *__restrict__ out,
 	       int D, int H, int W, int ld, int direction, int dch)
 {
-	using C = WSCfg<R, WS_HO>;
-	constexpr int WS_NT = ws_nt(WS_NPW, WS_HO), WS_NWT = C::NWT;
+	using C = WSCfg<R, WS_HO, LEAN>;
+	constexpr int WS_NT = ws_nt(WS_NPW, WS_HO), WS_NWT = C::NWT, WS_NST = C::NST;
 	constexpr int HALO = C::HALO, HX = C::HX, TH = C::TH, NWALK = C::NWALK, TWP = WS_TWP;
 	extern __shared__ __align__(128) unsigned char ws_smem[];
 	uint32_t *winH = reinterpret_cast<uint32_t *>(ws_smem + C::OFF_WINH);   // [TH][WS_WW] right-image H words (32-bit form)
@@ -478,17 +480,17 @@ cbca_ws_kernel(const __grid_constant__ CUtensorMap tmap,
 	}
 }
 
-template <int R, int WB, bool CENTER, int VMODE, int NPW, int HO>
+template <int R, int WB, bool CENTER, int VMODE, int NPW, int HO, bool LEAN>
 int launch_ws(const CUtensorMap &tm, const uint32_t *hv, const float *vol, float *out, int D, int H, int W, int ld, int direction,
 	      cudaStream_t s)
 {
-	using C = WSCfg<R, HO>;
+	using C = WSCfg<R, HO, LEAN>;
 	constexpr int smem = VMODE == 2 ? C::SMEM_RING : C::SMEM_NORING;
 	static bool attr_done[64] = {false};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!attr_done[dev & 63]) {
-		ADC_CUDA(cudaFuncSetAttribute(cbca_ws_kernel<R, WB, CENTER, VMODE, NPW, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		ADC_CUDA(cudaFuncSetAttribute(cbca_ws_kernel<R, WB, CENTER, VMODE, NPW, HO, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 		attr_done[dev & 63] = true;
 	}
 	static const int dch_env = getenv("ADCENSUS_CBCA_DCH") ? atoi(getenv("ADCENSUS_CBCA_DCH")) : 0;   // tuning knob, not part of the ABI
@@ -497,7 +499,7 @@ int launch_ws(const CUtensorMap &tm, const uint32_t *hv, const float *vol, float
 	dch = adc_div_up(D, adc_div_up(D, dch));               // equal chunks (19 x 12 at D = 228)
 	const long HW = (long)H * W;
 	dim3 grid(adc_div_up(W, WS_TX), adc_div_up(H, WS_TY), adc_div_up(D, dch));
-	cbca_ws_kernel<R, WB, CENTER, VMODE, NPW, HO><<<grid, ws_nt(NPW, HO), smem, s>>>(tm, hv, hv + 2 * HW, hv + HW, hv + 3 * HW, vol, out, D, H, W, ld, direction, dch);
+	cbca_ws_kernel<R, WB, CENTER, VMODE, NPW, HO, LEAN><<<grid, ws_nt(NPW, HO), smem, s>>>(tm, hv, hv + 2 * HW, hv + HW, hv + 3 * HW, vol, out, D, H, W, ld, direction, dch);
 	ADC_CHECK_LAUNCH();
 	return 0;
 }
@@ -510,7 +512,7 @@ int adc_cbca_ws_max_halo() { return 4; }
 void adc_cbca_ws_box(int halo, int *box_w, int *box_h)
 {
 	*box_w = WS_TWP;
-	*box_h = halo <= 1 ? WSCfg<1, 32>::TH : WSCfg<4, 32>::TH;
+	*box_h = halo <= 1 ? WSCfg<1, 32, false>::TH : WSCfg<4, 32, false>::TH;
 }
 
 // hv: packed arms (adc_pack_arms_hv); tm: tensor map of `vol` with the box of adc_cbca_ws_box(halo)
@@ -523,13 +525,15 @@ int adc_cbca_ws(const CUtensorMap *tm, const uint32_t *hv, const float *vol, flo
 	static const int center = getenv("ADCENSUS_CBCA_CENTER") ? atoi(getenv("ADCENSUS_CBCA_CENTER")) : 1;
 	static const int vmode = getenv("ADCENSUS_CBCA_VMODE") ? atoi(getenv("ADCENSUS_CBCA_VMODE")) : 2;
 	static const int npw = getenv("ADCENSUS_CBCA_NPW") ? atoi(getenv("ADCENSUS_CBCA_NPW")) : 4;
-#define WS_GO(R_, WB_, C_, V_, N_, HO_) return launch_ws<R_, WB_, C_, V_, N_, HO_>(*tm, hv, vol, out, D, H, W, ld, direction, s)
+#define WS_GO(R_, WB_, C_, V_, N_, HO_) return launch_ws<R_, WB_, C_, V_, N_, HO_, false>(*tm, hv, vol, out, D, H, W, ld, direction, s)
 	static const int ho = getenv("ADCENSUS_CBCA_HO") ? atoi(getenv("ADCENSUS_CBCA_HO")) : 32;
 	if (halo <= 1) {
 		if (vmode == 2) { if (center) WS_GO(1, 6, true, 2, 4, 32); else WS_GO(1, 6, false, 2, 4, 32); }
 		if (center) WS_GO(1, 6, true, 1, 4, 32); else WS_GO(1, 6, false, 1, 4, 32);
 	}
 	if (halo <= 4) {
+		static const int lean = getenv("ADCENSUS_CBCA_LEAN") ? atoi(getenv("ADCENSUS_CBCA_LEAN")) : 0;
+		if (lean && vmode == 2 && center) return launch_ws<4, 4, true, 2, 4, 32, true>(*tm, hv, vol, out, D, H, W, ld, direction, s);
 		if (ho == 16) {                                    // 16 walker warps (column x quarter), ring mode only
 			if (center) WS_GO(4, 4, true, 2, 3, 16); else WS_GO(4, 4, false, 2, 3, 16);
 		}
