@@ -211,6 +211,187 @@ conv3x3_umma_kernel(const FTParams p)
 	}
 }
 
+// ---- second form, for Cin = fm <= 64 (the fast architecture): weights RESIDENT, persistent CTAs --------------------------
+// The streamed form above is latency-bound (tensor pipe 5 % active at fm = 64: every tile waits for 72 weight slabs and for two
+// 40-chunk operand builds).  With 64 planes the whole layer's weights, split, are 147 KB: they stay in shared memory for the
+// life of a persistent CTA; the A operand is built one TAP at a time (K = 64: 32 KB for hi + lo) into a double buffer, so the
+// eight builder warps (next tap's loads already in flight while the current one is split and stored), the MMA thread and the
+// four epilogue warps (two accumulator stages in TMEM) all overlap.
+constexpr int F2_NB = 256, F2_NE = 128, F2_NT = F2_NB + F2_NE + 32;      // builders, epilogue, MMA warp
+constexpr int F2_WBYTES = 9 * 64 / 16 * 2 * 64 * 32;                       // 147456: 36 K steps x (hi, lo) x [2][64][8] bf16
+constexpr int F2_ABUF = 2 * (64 / 8) * SH_ACHUNK;                         // one tap: hi + lo = 32768
+constexpr int F2_OFF_A = F2_WBYTES, F2_OFF_BIAS = F2_OFF_A + 2 * F2_ABUF;
+constexpr int F2_OFF_BAR = F2_OFF_BIAS + 64 * 4;                           // a_full[2], a_free[2], acc_full[2], acc_free[2]
+constexpr int F2_OFF_TPTR = F2_OFF_BAR + 8 * 8;
+constexpr int F2_SMEM = F2_OFF_TPTR + 16;
+static_assert(F2_SMEM <= 232448, "shared memory budget");
+
+template <int NTERMS>
+__global__ void __launch_bounds__(F2_NT, 1)
+conv3x3_resident_kernel(const FTParams p, int nimg)
+{
+	extern __shared__ __align__(128) unsigned char ft_smem[];
+	unsigned char *wsm = ft_smem, *abuf = ft_smem + F2_OFF_A;
+	float *bias = reinterpret_cast<float *>(ft_smem + F2_OFF_BIAS);
+	uint64_t *a_full = reinterpret_cast<uint64_t *>(ft_smem + F2_OFF_BAR), *a_free = a_full + 2;
+	uint64_t *acc_full = a_free + 2, *acc_free = acc_full + 2;
+	uint32_t *tptr = reinterpret_cast<uint32_t *>(ft_smem + F2_OFF_TPTR);
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int H = p.H, W = p.W, Cin = p.Cin, Np = p.Np;           // Cin == 64, Np == 64
+	const long HW = (long)H * W;
+	const int xt = (W + SH_M - 1) / SH_M;
+	const int ntile = nimg * H * xt;
+	const int nks_tap = Cin / 16;
+	const uint32_t slab = (uint32_t)Np * 32u;
+
+	if (tid == 0) {
+		for (int i = 0; i < 2; i++) {
+			mbar_init(&a_full[i], F2_NB);
+			mbar_init(&a_free[i], 1);
+			mbar_init(&acc_full[i], 1);
+			mbar_init(&acc_free[i], F2_NE);
+		}
+		mbar_fence_init();
+	}
+	{   // the layer's weights: a straight copy of the prepared slabs
+		const uint4 *src = reinterpret_cast<const uint4 *>(p.wslabs);
+		uint4 *dst = reinterpret_cast<uint4 *>(wsm);
+		const int n16 = 9 * nks_tap * 2 * (int)slab / 16;
+		for (int i = tid; i < n16; i += F2_NT) dst[i] = __ldg(src + i);
+	}
+	for (int i = tid; i < 64; i += F2_NT) bias[i] = i < p.fm ? p.bias[i] : 0.0f;
+	if (warp == 12) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma_smem_addr(tptr)), "r"(128) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	fence_proxy_async_smem();                                  // the weights were written with generic stores
+	sh_fence_before();
+	__syncthreads();
+	sh_fence_after();
+	const uint32_t tbase = *tptr;
+
+	if (warp < 8) {
+		// ------------------------------------------------------------ operand builders: thread = (pixel m, 4 of the tap's 8 chunks)
+		const int m = tid & 127, hf = tid >> 7;
+		float nxt[4][8];
+		auto load = [&](int tile, int tap, float (&v)[4][8]) {
+			const int img = tile / (H * xt), rem = tile - img * (H * xt), y = rem / xt, x = (rem - y * xt) * SH_M + m;
+			const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+			const bool ok = tile < ntile && yy >= 0 && yy < H && xx >= 0 && xx < W;
+			const float *src = p.in + (long)img * Cin * HW + (long)(hf * 32) * HW + (long)(ok ? yy : 0) * W + (ok ? xx : 0);
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+#pragma unroll
+				for (int e = 0; e < 8; e++) v[u][e] = ok ? __ldg(src + (long)(u * 8 + e) * HW) : 0.0f;
+		};
+		unsigned g = 0;
+		int tile = blockIdx.x, tap = 0;
+		if (tile < ntile) load(tile, 0, nxt);
+		while (tile < ntile) {
+			float cur[4][8];
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+#pragma unroll
+				for (int e = 0; e < 8; e++) cur[u][e] = nxt[u][e];
+			int ntile_i = tile, ntap = tap + 1;                 // the step after this one
+			if (ntap == 9) { ntap = 0; ntile_i = tile + gridDim.x; }
+			load(ntile_i, ntap, nxt);                           // in flight while this step is split and stored
+			const int b = g & 1;
+			if (g >= 2) sh_wait(&a_free[b], ((g >> 1) - 1) & 1);
+			unsigned char *ah = abuf + b * F2_ABUF, *al = ah + (64 / 8) * SH_ACHUNK;
+#pragma unroll
+			for (int u = 0; u < 4; u++) sh_store8<NTERMS>(ah, al, hf * 4 + u, m, cur[u]);
+			fence_proxy_async_smem();
+			sh_fence_before();
+			sh_arrive(&a_full[b]);
+			g++;
+			tile = ntile_i;
+			tap = ntap;
+		}
+	} else if (warp == 12) {
+		// ------------------------------------------------------------ MMA issuer
+		if (lane == 0) {
+			const uint32_t a_s = tma_smem_addr(abuf), w_s = tma_smem_addr(wsm);
+			const uint32_t lbo_b = (uint32_t)Np * 16u, idesc = sh_idesc(Np);
+			unsigned g = 0, ti = 0;
+			for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, ti++) {
+				const int st = ti & 1;
+				if (ti >= 2) sh_wait(&acc_free[st], ((ti >> 1) - 1) & 1);
+				sh_fence_after();
+				for (int tap = 0; tap < 9; tap++, g++) {
+					const int b = g & 1;
+					sh_wait(&a_full[b], (g >> 1) & 1);
+					sh_fence_after();
+					for (int ks = 0; ks < nks_tap; ks++) {
+						const uint64_t da_hi = sh_desc(a_s + b * F2_ABUF + ks * 2 * SH_ACHUNK, SH_ACHUNK, 128);
+						const uint64_t da_lo = sh_desc(a_s + b * F2_ABUF + (64 / 8) * SH_ACHUNK + ks * 2 * SH_ACHUNK, SH_ACHUNK, 128);
+						const uint32_t wk = w_s + (uint32_t)(tap * nks_tap + ks) * 2u * slab;
+						const uint64_t db_hi = sh_desc(wk, lbo_b, 128), db_lo = sh_desc(wk + slab, lbo_b, 128);
+						const uint32_t acc_on = (tap > 0 || ks > 0) ? 1u : 0u;
+						sh_mma(tbase + st * 64, da_hi, db_hi, idesc, acc_on);
+						if (NTERMS == 3) {
+							sh_mma(tbase + st * 64, da_lo, db_hi, idesc, 1);
+							sh_mma(tbase + st * 64, da_hi, db_lo, idesc, 1);
+						}
+					}
+					sh_commit(&a_free[b]);
+				}
+				sh_commit(&acc_full[st]);
+			}
+		}
+	} else {
+		// ------------------------------------------------------------ epilogue warps 8-11: thread = pixel = TMEM lane
+		const int q = warp & 3, m = q * 32 + lane;
+		unsigned ti = 0;
+		for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, ti++) {
+			const int st = ti & 1;
+			const int img = tile / (H * xt), rem = tile - img * (H * xt), y = rem / xt, x = (rem - y * xt) * SH_M + m;
+			sh_wait(&acc_full[st], (ti >> 1) & 1);
+			sh_fence_after();
+			const uint32_t trow = tbase + ((uint32_t)(q * 32) << 16) + st * 64;
+			uint32_t r0[32], r1[32];
+			sh_tmem_ld32(trow, r0);
+			sh_tmem_ld32(trow + 32, r1);
+			sh_tmem_wait(r0);
+			sh_tmem_wait(r1);
+			sh_fence_before();
+			sh_arrive(&acc_free[st]);                             // the accumulator stage is in registers: the MMAs may reuse it
+			float z[64];
+#pragma unroll
+			for (int e = 0; e < 32; e++) {
+				z[e] = __uint_as_float(r0[e]) + bias[e];
+				z[32 + e] = __uint_as_float(r1[e]) + bias[32 + e];
+			}
+			if (p.relu) {
+#pragma unroll
+				for (int e = 0; e < 64; e++) z[e] = fmaxf(z[e], 0.0f);
+			}
+			if (p.normalize) {
+				float sum = 0.0f;
+#pragma unroll
+				for (int e = 0; e < 64; e++)
+					if (e < p.fm) sum = fmaf(z[e], z[e], sum);          // adcensus.cu:1293, planes ascending
+				const float scale = sqrtf(sum + 1e-5f);                 // :1296, :1305
+#pragma unroll
+				for (int e = 0; e < 64; e++) z[e] = z[e] / scale;
+			}
+			if (x < W) {
+				float *dst = p.out + (long)img * p.fm * HW + (long)y * W + x;
+#pragma unroll
+				for (int e = 0; e < 64; e++)
+					if (e < p.fm) dst[(long)e * HW] = z[e];
+			}
+		}
+	}
+	sh_fence_before();
+	__syncthreads();
+	if (warp == 12) {
+		sh_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(128) : "memory");
+	}
+}
+
 // first layer (Cin = 1 or 3): exact fp32, thread = pixel, weights in shared memory; planes / rows / columns ascending
 __global__ void conv3x3_first_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ b,
 				     float *__restrict__ out, int Cin, int fm, int H, int W, int relu)
@@ -358,6 +539,27 @@ extern "C" int mccnn_feature_tower_forward(const mccnn_feature_tower *h, const f
 		p.taps_per_pass = FT_KA / h->fm;                       // K of a pass = taps x Cin <= 320
 		if (p.taps_per_pass > 9) p.taps_per_pass = 9;
 		const dim3 grid(adc_div_up(W, SH_M), H, nimg);
+		static const int resident_ok = getenv("ADCENSUS_TOWER_RESIDENT") ? atoi(getenv("ADCENSUS_TOWER_RESIDENT")) : 1;   // tuning knob
+		if (resident_ok && h->fm == 64) {                          // weights resident, persistent CTAs (the fast architecture)
+			static bool attr_r3[64] = {false}, attr_r1[64] = {false};
+			const int ntile = nimg * H * adc_div_up(W, SH_M);
+			const int nb = ntile < adc_num_sms() ? ntile : adc_num_sms();
+			if (nterms == 3) {
+				if (!attr_r3[dev & 63]) {
+					rc = (int)cudaFuncSetAttribute(conv3x3_resident_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);
+					attr_r3[dev & 63] = true;
+				}
+				if (!rc) conv3x3_resident_kernel<3><<<nb, F2_NT, F2_SMEM, s>>>(p, nimg);
+			} else {
+				if (!attr_r1[dev & 63]) {
+					rc = (int)cudaFuncSetAttribute(conv3x3_resident_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);
+					attr_r1[dev & 63] = true;
+				}
+				if (!rc) conv3x3_resident_kernel<1><<<nb, F2_NT, F2_SMEM, s>>>(p, nimg);
+			}
+			if (!rc) rc = (int)cudaPeekAtLastError();
+			continue;
+		}
 		if (nterms == 3) {
 			if (!attr3[dev & 63]) {
 				rc = (int)cudaFuncSetAttribute(conv3x3_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
