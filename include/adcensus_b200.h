@@ -71,8 +71,9 @@ int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1
 int adcensus_cbca(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 		  int D, int H, int W, int direction, adcensus_stream_t stream);
 
-/* Same, without the host synchronisation: the caller states the longest arm cross() can have
- * produced for these arms, max(L1, 2) (main.lua knows opt.L1).  Asynchronous on `stream`. */
+/* Same with the kernel chosen on the host: the caller states the longest arm cross() can have produced for these arms,
+ * max(L1, 2) (main.lua knows opt.L1).  Arms longer than max_arm (<= 14) are CUT at max_arm (a truncated support, never an
+ * out-of-bounds read); state the true bound or use adcensus_cbca.  Asynchronous on `stream`. */
 int adcensus_cbca_ex(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 		     int D, int H, int W, int direction, int max_arm, adcensus_stream_t stream);
 

@@ -52,7 +52,9 @@ __global__ void cross_kernel(const float *__restrict__ img, float *__restrict__ 
 
 // ------------------------------------------------------------------ arm packing
 // word = L | R<<8 | U<<16 | D<<24 with L = x - left end-point etc. (all >= 1 for arms made by cross)
-__global__ void pack_arms_kernel(const float *__restrict__ xc, uint32_t *__restrict__ packed, int H, int W, int *maxlen)
+// clamp > 0: lengths are cut at `clamp` (the caller's stated longest arm): the window / tile kernels size their shared-memory
+// walks by it, so an understated bound gives a truncated support instead of an out-of-bounds read
+__global__ void pack_arms_kernel(const float *__restrict__ xc, uint32_t *__restrict__ packed, int H, int W, int *maxlen, int clamp)
 {
 	int id = blockIdx.x * blockDim.x + threadIdx.x;
 	int HW = H * W;
@@ -66,8 +68,9 @@ __global__ void pack_arms_kernel(const float *__restrict__ xc, uint32_t *__restr
 		m = max(max(l, r), max(u, d));
 		int lo = min(min(l, r), min(u, d));
 		if (lo < 0) m = 1 << 20;  // not a cross() output: force the generic kernel
-		l = min(max(l, 0), 255); r = min(max(r, 0), 255);
-		u = min(max(u, 0), 255); d = min(max(d, 0), 255);
+		const int hi = clamp > 0 ? min(clamp, 255) : 255;
+		l = min(max(l, 0), hi); r = min(max(r, 0), hi);
+		u = min(max(u, 0), hi); d = min(max(d, 0), hi);
 		packed[id] = (uint32_t)l | ((uint32_t)r << 8) | ((uint32_t)u << 16) | ((uint32_t)d << 24);
 	}
 	m = __reduce_max_sync(0xffffffffu, m);
@@ -442,12 +445,17 @@ void launch_tile(const uint32_t *a0, const uint32_t *a1, const float *vol, float
 // packed buffer layout (uint32 words, HW = H*W): [image 0 | image 1]
 size_t adc_packed_words(int H, int W) { return 2 * (size_t)H * W; }
 
-int adc_pack_arms(const float *xc, uint32_t *pk, int which, int H, int W, int *maxlen_dev, cudaStream_t s)
+static int pack_arms(const float *xc, uint32_t *pk, int which, int H, int W, int *maxlen_dev, int clamp, cudaStream_t s)
 {
 	const long HW = (long)H * W;
-	pack_arms_kernel<<<adc_div_up(HW, 256), 256, 0, s>>>(xc, pk + which * HW, H, W, maxlen_dev);
+	pack_arms_kernel<<<adc_div_up(HW, 256), 256, 0, s>>>(xc, pk + which * HW, H, W, maxlen_dev, clamp);
 	ADC_CHECK_LAUNCH();
 	return 0;
+}
+
+int adc_pack_arms(const float *xc, uint32_t *pk, int which, int H, int W, int *maxlen_dev, cudaStream_t s)
+{
+	return pack_arms(xc, pk, which, H, W, maxlen_dev, 0, s);
 }
 
 // Exact (bit-identical) aggregation.  maxlen = longest arm (distance to the exclusive end-point) of either
@@ -522,8 +530,9 @@ extern "C" int adcensus_cbca_ex(const float *x0c, const float *x1c, const float 
 	if (rc) return rc;
 	int *maxlen_dev = (int *)(packed + adc_packed_words(H, W));
 	rc = (int)cudaMemsetAsync(maxlen_dev, 0, sizeof(int), s);
-	if (!rc) rc = adc_pack_arms(x0c, packed, 0, H, W, maxlen_dev, s);
-	if (!rc) rc = adc_pack_arms(x1c, packed, 1, H, W, maxlen_dev, s);
+	const int clamp = max_arm <= 14 ? max_arm : 0;            // beyond 14 the generic kernel reads the float arms themselves
+	if (!rc) rc = pack_arms(x0c, packed, 0, H, W, maxlen_dev, clamp, s);
+	if (!rc) rc = pack_arms(x1c, packed, 1, H, W, maxlen_dev, clamp, s);
 	if (!rc) rc = adc_cbca_packed(packed, x0c, x1c, vol_in, vol_out, D, H, W, W, direction, max_arm, s);
 	int rc2 = adc_scratch_free(packed, s);
 	return rc ? rc : rc2;
