@@ -435,6 +435,7 @@ def test_against_live_reference():
 @pytest.mark.parametrize("H,W,C,D,preset,over", [
     (370, 1226, 64, 228, ("kitti", "accurate_cbca4"), {}),      # BASELINE config 3, the bench workload
     (370, 1226, 64, 70, ("kitti2015", "slow"), {}),             # d = 70 with CBCA x 6 (cbca_i1 = 2, cbca_i2 = 4)
+    (300, 700, 32, 128, ("mb", "slow"), dict(cbca_i2=4)),       # Middlebury preset: arms up to 14 pixels (first-generation kernel)
 ])
 def test_full_size_default_mode_against_live_reference(H, W, C, D, preset, over):
     """The pipeline's DEFAULT mode (constant-work CBCA) at BASELINE.json's full size against the reference's own kernels on
@@ -539,6 +540,8 @@ FULL_SIZE = [
     # BASELINE.json config 2 (KITTI fast, d=70) and config 3 (KITTI accurate, d=228, CBCA x4 + SGM)
     (370, 1226, 64, 70, ("kitti", "fast"), {}),
     (370, 1226, 64, 228, ("kitti", "accurate_cbca4"), {}),
+    # Middlebury preset at a moderate size: L1 = 14 (halo 13: the tile kernels of the exact mode), no LR check
+    (300, 700, 32, 128, ("mb", "slow"), dict(cbca_i2=4)),
 ]
 
 
@@ -568,7 +571,8 @@ def test_full_size_against_live_reference(H, W, C, D, preset, over):
     # size-independent properties of the domain at full size
     d = disp.cpu().numpy()
     assert not np.isnan(d).any() and d.min() >= 0 and d.max() <= D - 1 + 1e-3          # main.lua:1224
-    assert (np.abs(d - p["gt"]) < 1.0).mean() > 0.6                                    # recovers the synthetic GT
+    if opt.lr_check:
+        assert (np.abs(d - p["gt"]) < 1.0).mean() > 0.6                                # recovers the synthetic GT
     vl = volL[:, H // 2, :].cpu().numpy()
     for dd in range(0, D, 37):                                                         # NaN triangle intact
         assert np.isnan(vl[dd, :dd]).all() and not np.isnan(vl[dd, dd:]).any()
