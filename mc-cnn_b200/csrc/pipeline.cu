@@ -339,7 +339,13 @@ extern "C" int mccnn_pipeline_run(mccnn_pipeline *p, const float *featL, const f
 	// fix_border copies column W-n-1 over the border columns: for D > W - n - 1 that column holds NaN at "valid"
 	// positions, which only the tap-by-tap generic kernel treats like the reference (NaN only where a tap is NaN)
 	const bool nan_in_valid = o.border > 0 && D > W - o.border - 1;
-	const bool tma = p->cbca_mode && !nan_in_valid && maxlen - 1 <= adc_cbca_tma_max_halo() && p->ntm > 0;
+	// constant-work aggregation only for arms <= 5 (the KITTI presets, cbca_ws.cu): with the Middlebury presets' arms of up to
+	// 14 pixels the first-generation kernel's float prefixes over 27 x 27 windows reach 1.03e-4 after six iterations (measured,
+	// mb slow at 300 x 700 x 128) -- outside the 1e-4 contract -- so those presets run the exact tile kernels in every mode
+	// (ADCENSUS_CBCA_FAST_LONG=1 overrides)
+	static const bool fast_long = getenv("ADCENSUS_CBCA_FAST_LONG") && atoi(getenv("ADCENSUS_CBCA_FAST_LONG"));
+	const int fast_halo = fast_long ? adc_cbca_tma_max_halo() : 4;
+	const bool tma = p->cbca_mode && !nan_in_valid && maxlen - 1 <= fast_halo && p->ntm > 0;
 	uint32_t *hv = p->packed + adc_packed_words(H, W);
 	if (ncbca > 0) {
 		STEP(adcensus_cross(imgL, p->x0c, H, W, o.L1, o.tau1, s));
