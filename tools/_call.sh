@@ -1,8 +1,5 @@
 set -u
 mkdir -p gpurun_out
-timeout 1800 python -m pytest tests -m gpu -q -rfs 2>&1 > gpurun_out/r2_final2_tests_full.log
-grep -E "^FAILED|^SKIPPED|passed|failed|^E  " gpurun_out/r2_final2_tests_full.log | head -20
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['modes']['exact']['value'])"
+timeout 1800 python -m pytest tests -m gpu -q -rfs 2>&1 > gpurun_out/r2_final3_tests_full.log
+grep -E "^FAILED|^SKIPPED|passed|failed|^E  " gpurun_out/r2_final3_tests_full.log | head -12
+for i in 1 2 3; do timeout 300 python -m pytest tests/test_gpu_sgm_dhw.py tests/test_gpu_parity.py -m gpu -q -x -k "sgm or default_mode" 2>&1 | tail -1; done
