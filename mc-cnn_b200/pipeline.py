@@ -82,12 +82,14 @@ def make_params(dataset="kitti", arch="fast", **overrides):
     return Params(**d)
 
 
-def stereo_predict(x_batch, features, opt, disp_max, want_vols=False, arch="fast"):
+def stereo_predict(x_batch, features, opt, disp_max, want_vols=False, arch="fast", head=None):
     """main.lua:929-1082 through the adcensus.* operators.
 
     x_batch  (2,1,H,W) standardised images (left, right); arch 'fast': features (2,C,H,W) the tower
     output (unit-norm); arch 'ad' / 'census': the matching cost comes from the images themselves
-    (main.lua:932-942), `features` is ignored.  opt a :class:`Params`.
+    (main.lua:932-942), `features` is ignored; arch 'slow' (main.lua:956-981): features (2,fm,H,W) = the accurate
+    architecture's tower output and `head` a :class:`mccnn_b200.scorer_head.ScorerHead` (net_te2), which scores every
+    disparity into both volumes.  opt a :class:`Params`.
     Returns disp (1,1,H,W) [, left vol, right vol].
     """
     assert x_batch.is_cuda
@@ -106,8 +108,15 @@ def stereo_predict(x_batch, features, opt, disp_max, want_vols=False, arch="fast
         adcensus.StereoJoin(features[0:1], features[1:2], vols[0:1], vols[1:2])   # :947
         adcensus.fix_border(vols[0:1], opt.border, -1)                            # :948
         adcensus.fix_border(vols[1:2], opt.border, 1)                             # :949
+    elif arch == "slow":
+        assert features is not None and features.is_cuda and head is not None, "arch 'slow' needs the tower output and a ScorerHead"
+        vl, vr = head.volumes(features[0].contiguous(), features[1].contiguous(), disp_max)   # :962-979 (both directions at once)
+        vols[0:1].copy_(vl)
+        vols[1:2].copy_(vr)
+        adcensus.fix_border(vols[0:1], opt.border, -1)                            # :981
+        adcensus.fix_border(vols[1:2], opt.border, 1)
     else:
-        raise ValueError("arch must be 'fast', 'ad' or 'census' (the 'slow' scorer head is outside libadcensus)")
+        raise ValueError("arch must be 'fast', 'slow', 'ad' or 'census'")
 
     disp = {}
     out_vols = {}

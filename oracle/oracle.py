@@ -262,7 +262,7 @@ def stereo_predict(featL, featR, imgL, imgR, D, params, want_vols=False):
     return (disp, volL, volR) if want_vols else disp
 
 
-def stereo_predict_chain(imgL, imgR, D, params, arch="fast", featL=None, featR=None, want_vols=False):
+def stereo_predict_chain(imgL, imgR, D, params, arch="fast", featL=None, featR=None, want_vols=False, volL=None, volR=None):
     """main.lua:929-1082 composed from the per-operator oracle functions (the C `orc_stereo_predict`
     is the same chain for arch 'fast' in one call; tests/test_oracle_properties.py checks that the
     two agree).  arch 'ad' / 'census' (main.lua:932-942) build the volumes from the images.
@@ -277,6 +277,10 @@ def stereo_predict_chain(imgL, imgR, D, params, arch="fast", featL=None, featR=N
         volL, volR = stereo_join(featL, featR, D)                                  # :946-947
         fix_border(volL, params.border, -1)                                        # :948
         fix_border(volR, params.border, 1)                                         # :949
+    elif arch == "volumes":                                                        # arch 'slow': the scorer head's volumes (:962-979) are given
+        volL, volR = np.array(volL, np.float32, copy=True), np.array(volR, np.float32, copy=True)
+        fix_border(volL, params.border, -1)                                        # :981
+        fix_border(volR, params.border, 1)
     else:
         raise ValueError(arch)
     x0c, x1c = cross(imgL, params.L1, params.tau1), cross(imgR, params.L1, params.tau1)   # :995-996

@@ -68,3 +68,31 @@ def test_rejects_unsupported_shapes():
     rng = np.random.default_rng(0)
     with pytest.raises(Exception):
         scorer_head.ScorerHead(osh.make_weights(rng, 8, 100, 2))       # nh2 not a multiple of 128
+
+
+def test_arch_slow_chain_from_images(oracle):
+    """main.lua's arch 'slow' flow end to end on the GPU: images -> feature tower (tcgen05) -> scorer head (tcgen05) ->
+    fix_border -> cross / cbca / sgm2 / post (pipeline.stereo_predict(arch='slow')).  The stages after the head are integer /
+    exact-order work: from the head's own volumes they must equal the oracle chain bit for bit."""
+    from mccnn_b200 import feature_tower, pipeline, synth
+    from oracle import feature_tower as oft
+
+    H, W, D, fm, nh2 = 40, 150, 24, 16, 128
+    rng = np.random.default_rng(3)
+    p = synth.make_pair(H, W, 4, D, seed=9)
+    x = np.stack([p["imgL"], p["imgR"]])[:, None].astype(np.float32)
+    tower = feature_tower.FeatureTower(oft.make_weights(rng, l1=3, fm=fm), arch="slow")
+    head = scorer_head.ScorerHead(osh.make_weights(rng, fm, nh2, 2))
+    opt = pipeline.make_params("kitti", "slow")
+    xb = cu(x)
+    feats = tower.forward(xb)
+    disp, vl, vr = pipeline.stereo_predict(xb, feats, opt, D, want_vols=True, arch="slow", head=head)
+    hl, hr = head.volumes(feats[0].contiguous(), feats[1].contiguous(), D)
+    torch.cuda.synchronize()
+    want, wl, wr = oracle.stereo_predict_chain(p["imgL"], p["imgR"], D, oracle.Params(**opt.as_dict()), arch="volumes",
+                                               volL=hl[0].cpu().numpy(), volR=hr[0].cpu().numpy(), want_vols=True)
+    for got, ref, what in ((vl, wl, "left volume"), (vr, wr, "right volume"), (disp, want, "disparity map")):
+        g = got.cpu().numpy().reshape(ref.shape)
+        assert np.array_equal(g, ref, equal_nan=True), what + " differs from the oracle chain"
+    tower.close()
+    head.close()

@@ -139,3 +139,18 @@ def test_ad_census_chain_invariants(oracle):
         assert disp.shape == (H, W) and not np.isnan(disp).any()
         assert disp.min() >= 0 and disp.max() <= D - 1 + 1e-3
         assert (np.abs(disp[:, 2 * D:] - shift) < 1.0).mean() > 0.9, arch
+
+
+def test_chain_from_given_volumes_equals_the_fast_arch_chain(oracle):
+    """arch 'volumes' (the accurate architecture's entry: the scorer head's volumes are given, main.lua:981 onwards) is the same
+    chain as arch 'fast' after StereoJoin"""
+    import mccnn_b200  # noqa: F401
+    from mccnn_b200 import pipeline, synth
+
+    H, W, C, D = 20, 44, 4, 9
+    p = synth.make_pair(H, W, C, D, seed=21)
+    opt = oracle.Params(**pipeline.make_params("kitti", "slow").as_dict())
+    a = oracle.stereo_predict_chain(p["imgL"], p["imgR"], D, opt, arch="fast", featL=p["featL"], featR=p["featR"])
+    vl, vr = oracle.stereo_join(p["featL"], p["featR"], D)
+    b = oracle.stereo_predict_chain(p["imgL"], p["imgR"], D, opt, arch="volumes", volL=vl, volR=vr)
+    assert np.array_equal(a, b, equal_nan=True)
