@@ -77,11 +77,13 @@ def write_bin(path, t):
 
 
 def predict(left, right, dataset="kitti", arch="census", disp_max=70, features=None, out_dir=None, device=0,
-            **overrides):
-    """``main.lua <dataset> <arch> -a predict -left L -right R -disp_max D`` from the image batch on:
+            net_fname=None, **overrides):
+    """``main.lua <dataset> <arch> -a predict -net_fname N -left L -right R -disp_max D`` from the image files on:
     returns disp (H,W) float32 (numpy).  With `out_dir`, writes right.bin and left.bin ((1,D,H,W), in
-    that order, main.lua:1042-1047) and disp.bin ((1,1,H,W), :1103) there.  arch 'fast' needs
-    `features` (2,C,H,W), the unit-norm tower output; 'ad' / 'census' need none."""
+    that order, main.lua:1042-1047) and disp.bin ((1,1,H,W), :1103) there.  arch 'fast' / 'slow' take the trained
+    network from `net_fname` (the reference's ascii .t7, main.lua:893-901, read by :mod:`t7`) and run it on the GPU
+    (feature tower, and for 'slow' the scorer head); arch 'fast' alternatively accepts `features` (2,C,H,W), the
+    unit-norm tower output; 'ad' / 'census' need neither."""
     import torch
 
     from . import pipeline
@@ -89,12 +91,28 @@ def predict(left, right, dataset="kitti", arch="census", disp_max=70, features=N
     batch = make_batch(left, right)
     dev = torch.device("cuda", device)
     x_batch = torch.from_numpy(batch).to(dev)
-    feats = None
-    if arch == "fast":
-        assert features is not None, "arch 'fast' needs the feature tower's output"
+    feats = head = None
+    if arch in ("fast", "slow") and features is None:
+        if net_fname is None:
+            raise ValueError("arch '%s' needs -net_fname (or, for 'fast', the tower output in `features`)" % arch)
+        from . import t7
+        from .feature_tower import FeatureTower
+        from .scorer_head import ScorerHead
+
+        net = t7.load_net(net_fname)
+        if net.arch != arch:
+            raise ValueError("%s holds a '%s' network, arch '%s' was asked for" % (net_fname, net.arch, arch))
+        with torch.cuda.device(dev):
+            feats = FeatureTower(net.tower, arch=arch, device=dev.index).forward(x_batch)      # main.lua:944 / :957
+            if arch == "slow":
+                head = ScorerHead(net.head, device=dev.index)                                  # net_te2, main.lua:896
+    elif arch == "fast":
         feats = torch.as_tensor(features, dtype=torch.float32).to(dev).contiguous()
+    elif arch == "slow":
+        raise ValueError("arch 'slow' needs -net_fname: the scorer head's weights come with the tower's")
     opt = pipeline.make_params(dataset, arch, **overrides)
-    disp, volL, volR = pipeline.stereo_predict(x_batch, feats, opt, int(disp_max), want_vols=True, arch=arch)
+    with torch.cuda.device(dev):
+        disp, volL, volR = pipeline.stereo_predict(x_batch, feats, opt, int(disp_max), want_vols=True, arch=arch, head=head)
     disp_h = disp.cpu().numpy()
     if out_dir is not None:
         os.makedirs(out_dir, exist_ok=True)
