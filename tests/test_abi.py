@@ -59,6 +59,30 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
     assert lib.adcensus_cbca(one, one, one, one, 4, 4, 4, 1, None) == -1                   # in aliases out
 
 
+def test_round2_entry_points_reject_bad_arguments_without_a_gpu(lib):
+    """scorer head / feature tower / batch call: EINVAL (-1) for null or nonsensical arguments, ELIMIT (-2) for shapes the
+    kernels are not built for -- all decided before the first CUDA call"""
+    h = ctypes.c_void_p()
+    arr = (ctypes.c_void_p * 5)(*[16] * 5)
+    lib.mccnn_scorer_head_create.restype = lib.mccnn_feature_tower_create.restype = ctypes.c_int
+    sh = lambda fm, nh2, l2, W=arr, b=arr: lib.mccnn_scorer_head_create(ctypes.byref(h), fm, nh2, l2, W, b, 0, None)
+    assert sh(112, 384, 3, None) == -1 and sh(112, 384, 3, arr, None) == -1
+    assert lib.mccnn_scorer_head_create(None, 112, 384, 3, arr, arr, 0, None) == -1
+    assert sh(112, 384, 0) == -1 and sh(4, 384, 3) == -1 and sh(112, 64, 3) == -1
+    assert sh(112, 200, 3) == -2                                   # nh2 must be a multiple of 128
+    assert sh(108, 384, 3) == -2                                   # fm must be a multiple of 8
+    assert sh(112, 384, 9) == -2                                   # more hidden layers than the kernel unrolls
+    assert h.value is None
+    ft = lambda n_in, fm, l1, W=arr, b=arr: lib.mccnn_feature_tower_create(ctypes.byref(h), n_in, fm, l1, 0, 1, W, b, 0, None)
+    assert ft(1, 64, 4, None) == -1 and ft(2, 64, 4) == -1 and ft(1, 64, 0) == -1 and ft(1, 4, 4) == -1
+    assert ft(1, 72, 4) == -2                                      # fm must be a multiple of 16
+    assert ft(1, 64, 40) == -2
+    assert h.value is None
+    assert lib.mccnn_scorer_head_forward(None, arr, arr, arr, arr, 4, 4, 4, 3, None) == -1
+    assert lib.mccnn_feature_tower_forward(None, arr, arr, 2, 4, 4, 3, None) == -1
+    assert lib.mccnn_pipeline_run_batch(None, 1, arr, arr, arr, arr, arr, None) == -1
+
+
 def test_python_mirror_type_errors():
     import torch
 
