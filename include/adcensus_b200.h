@@ -67,7 +67,11 @@ int adcensus_cross(const float *x0, float *out, int H, int W, int L1, float tau1
 
 /* adcensus.cbca(x0c, x1c, vol_in, vol_out, direction)  adcensus.cu:343-400
  * vol_in must not alias vol_out.  Fully asynchronous: the longest arm, which sizes the shared-memory tile, stays on
- * the device -- every candidate kernel is launched with a gate on it and the ones out of range return immediately. */
+ * the device -- every candidate kernel is launched with a gate on it and the ones out of range return immediately.
+ * Precondition shared with the reference's (compiled-out) assert at adcensus.cu:366: vol_in is finite wherever a support can
+ * reach, i.e. on x >= d (direction -1) / x < W - d (direction 1) -- for a fix_border'ed volume that means D <= W - border - 1.
+ * Under it the result is bit-identical; a NaN inside the valid part spreads to the outputs of the tile rows that walk over it,
+ * not only to the supports that contain it. */
 int adcensus_cbca(const float *x0c, const float *x1c, const float *vol_in, float *vol_out,
 		  int D, int H, int W, int direction, adcensus_stream_t stream);
 
