@@ -88,28 +88,34 @@ def predict(left, right, dataset="kitti", arch="census", disp_max=70, features=N
 
     from . import pipeline
 
+    net = None
+    if arch in ("fast", "slow") and features is None:                          # decided before any GPU work
+        if net_fname is None:
+            raise ValueError("arch '%s' needs -net_fname (or, for 'fast', the tower output in `features`)" % arch)
+        from . import t7
+
+        net = t7.load_net(net_fname)                                            # main.lua:893-901
+        if net.arch != arch:
+            raise ValueError("%s holds a '%s' network, arch '%s' was asked for" % (net_fname, net.arch, arch))
+    elif arch == "slow":
+        raise ValueError("arch 'slow' needs -net_fname: the scorer head's weights come with the tower's")
+    elif arch not in ("fast", "ad", "census"):
+        raise ValueError("arch must be 'fast', 'slow', 'ad' or 'census'")
+
     batch = make_batch(left, right)
     dev = torch.device("cuda", device)
     x_batch = torch.from_numpy(batch).to(dev)
     feats = head = None
-    if arch in ("fast", "slow") and features is None:
-        if net_fname is None:
-            raise ValueError("arch '%s' needs -net_fname (or, for 'fast', the tower output in `features`)" % arch)
-        from . import t7
+    if net is not None:
         from .feature_tower import FeatureTower
         from .scorer_head import ScorerHead
 
-        net = t7.load_net(net_fname)
-        if net.arch != arch:
-            raise ValueError("%s holds a '%s' network, arch '%s' was asked for" % (net_fname, net.arch, arch))
         with torch.cuda.device(dev):
             feats = FeatureTower(net.tower, arch=arch, device=dev.index).forward(x_batch)      # main.lua:944 / :957
             if arch == "slow":
                 head = ScorerHead(net.head, device=dev.index)                                  # net_te2, main.lua:896
     elif arch == "fast":
         feats = torch.as_tensor(features, dtype=torch.float32).to(dev).contiguous()
-    elif arch == "slow":
-        raise ValueError("arch 'slow' needs -net_fname: the scorer head's weights come with the tower's")
     opt = pipeline.make_params(dataset, arch, **overrides)
     with torch.cuda.device(dev):
         disp, volL, volR = pipeline.stereo_predict(x_batch, feats, opt, int(disp_max), want_vols=True, arch=arch, head=head)

@@ -69,3 +69,26 @@ def test_write_bin_roundtrip(tmp_path):
     p = tmp_path / "x.bin"
     frontend.write_bin(str(p), t)
     assert p.stat().st_size == 96 and np.array_equal(np.fromfile(str(p), "<f4"), t.ravel())
+
+
+def test_predict_refuses_bad_net_arguments_before_any_gpu_work(tmp_path):
+    """main.lua:893-901: 'fast' / 'slow' load opt.net_fname; a missing file name, a net of the other architecture or an
+    unknown arch are errors -- raised on the host, before images are read or the device is touched"""
+    from mccnn_b200 import t7
+
+    rng = np.random.default_rng(0)
+    fast = str(tmp_path / "fast.t7")
+    t7.save_net(fast, [(rng.standard_normal((16, 1, 3, 3)).astype(np.float32), np.zeros(16, np.float32)),
+                       (rng.standard_normal((16, 16, 3, 3)).astype(np.float32), np.zeros(16, np.float32))])
+    with pytest.raises(ValueError, match="net_fname"):
+        frontend.predict("no-such-left.png", "no-such-right.png", "kitti", "fast", disp_max=8)
+    with pytest.raises(ValueError, match="'fast' network"):
+        frontend.predict("no-such-left.png", "no-such-right.png", "kitti", "slow", disp_max=8, net_fname=fast)
+    with pytest.raises(ValueError, match="needs -net_fname"):
+        frontend.predict("no-such-left.png", "no-such-right.png", "kitti", "slow", disp_max=8,
+                         features=np.zeros((2, 16, 4, 4), np.float32))
+    with pytest.raises(ValueError, match="arch must be"):
+        frontend.predict("no-such-left.png", "no-such-right.png", "kitti", "sad", disp_max=8)
+    with pytest.raises(t7.T7Error):
+        frontend.predict("no-such-left.png", "no-such-right.png", "kitti", "fast", disp_max=8,
+                         net_fname=str(_png(tmp_path, "x.png", np.zeros((4, 4), np.uint8), "L")))
